@@ -1,0 +1,199 @@
+"""ctypes binding of libgemotion_b200.so (include/gemotion_b200.h).
+
+This is the Python twin of the Julia `ccall` stub in INTEGRATION.md: same entry points, same
+argument meaning, rc != 0 -> exception (Gridap style).  There is no fallback: if the shared
+library or a B200 is missing every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libgemotion_b200.so")
+
+GM_QUAD, GM_TRI = 0, 1
+GM_LAYOUT_CSC, GM_LAYOUT_CSR = 0, 1
+GM_JACOBIAN, GM_RESIDUAL, GM_CHECK_FINITE = 1, 2, 4
+GM_PATH_AUTO, GM_PATH_SCATTER, GM_PATH_CART = 0, 1, 2
+
+EXPORTS = ["gm_version", "gm_last_error", "gm_create", "gm_destroy", "gm_set_params", "gm_pattern",
+           "gm_get_pattern", "gm_assemble", "gm_assemble_device", "gm_host_register", "gm_host_unregister",
+           "gm_set_stream", "gm_timing", "gm_info", "gm_nccl_unique_id", "gm_comm_init"]
+
+
+class GmError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("gemotion_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class gm_desc(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32), ("cell_type", C.c_int32),
+        ("ncells", C.c_int64), ("nverts", C.c_int64),
+        ("cartesian", C.c_int32), ("nx", C.c_int32), ("ny", C.c_int32),
+        ("origin", C.c_double * 2), ("h", C.c_double * 2),
+        ("coords", C.c_void_p), ("cell_vertices", C.c_void_p),
+        ("vertex_index_base", C.c_int32), ("layout", C.c_int32),
+        ("cell_dofs_u", C.c_void_p), ("cell_dofs_p", C.c_void_p), ("cell_dofs_t", C.c_void_p),
+        ("n_free", C.c_int64 * 3), ("n_diri", C.c_int64 * 3),
+        ("diri_u", C.c_void_p), ("diri_p", C.c_void_p), ("diri_t", C.c_void_p),
+        ("nq", C.c_int32), ("nn", C.c_int32), ("nv", C.c_int32),
+        ("w", C.c_void_p), ("phi", C.c_void_p), ("dphi", C.c_void_p), ("psi", C.c_void_p), ("dgphi", C.c_void_p),
+        ("device", C.c_int32), ("path", C.c_int32),
+        ("rank", C.c_int32), ("nranks", C.c_int32),
+        ("cell_begin", C.c_int64), ("ncells_global", C.c_int64),
+    ]
+
+
+class gm_times(C.Structure):
+    _fields_ = [("h2d_ms", C.c_double), ("kernel_ms", C.c_double), ("d2h_ms", C.c_double),
+                ("exchange_ms", C.c_double), ("launches", C.c_int64),
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
+
+
+_lib = None
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/ for sm_100a into libgemotion_b200.so (in-tree)."""
+    src = os.path.join(HERE, "csrc")
+    newest = max(os.path.getmtime(os.path.join(src, f)) for f in os.listdir(src))
+    newest = max(newest, os.path.getmtime(os.path.join(HERE, "..", "include", "gemotion_b200.h")))
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < newest:
+        subprocess.check_call(["make", "-C", src] + ([] if verbose else ["-s"]))
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GmError(-2, "libgemotion_b200.so not built (run __graft_entry__.build()); there is no CPU path")
+        L = C.CDLL(LIB_PATH)
+        L.gm_last_error.restype = C.c_char_p
+        L.gm_destroy.restype = None
+        for name in EXPORTS:
+            getattr(L, name)  # raises if a symbol is missing
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise GmError(rc, lib().gm_last_error().decode())
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Handle:
+    """Owns one gm_handle."""
+
+    def __init__(self, sp, layout="csc", device=0, path=GM_PATH_AUTO):
+        m, r = sp.model, sp.ref
+        c = np.ascontiguousarray
+        d = gm_desc()
+        d.struct_size = C.sizeof(gm_desc)
+        d.cell_type = m.cell_type
+        d.ncells, d.nverts = m.ncells, m.nverts
+        keep = {}
+        if m.cartesian:
+            d.cartesian = 1
+            d.nx, d.ny = m.partition
+            d.origin[0], d.origin[1] = m.origin
+            d.h[0], d.h[1] = m.h
+        else:
+            keep["coords"] = c(m.vertex_coords, dtype=np.float64)
+            keep["cv"] = c(m.cell_vertices, dtype=np.int32)
+            d.coords, d.cell_vertices = _p(keep["coords"]), _p(keep["cv"])
+        d.vertex_index_base = 0
+        d.layout = GM_LAYOUT_CSR if layout == "csr" else GM_LAYOUT_CSC
+        keep["du"], keep["dp"], keep["dt"] = c(sp.U.cell_dofs, dtype=np.int32), c(sp.cell_dofs_p, dtype=np.int32), c(sp.T.cell_dofs, dtype=np.int32)
+        d.cell_dofs_u, d.cell_dofs_p, d.cell_dofs_t = _p(keep["du"]), _p(keep["dp"]), _p(keep["dt"])
+        nd = [sp.U.diri_values.size, 1, sp.T.diri_values.size]
+        for i in range(3):
+            d.n_free[i] = int(sp.n_free[i])
+            d.n_diri[i] = int(nd[i])
+        keep["vu"], keep["vp"], keep["vt"] = c(sp.U.diri_values), c(sp.diri_p), c(sp.T.diri_values)
+        d.diri_u = _p(keep["vu"]) if nd[0] else None
+        d.diri_p = _p(keep["vp"])
+        d.diri_t = _p(keep["vt"]) if nd[2] else None
+        d.nq, d.nn, d.nv = r.nq, r.nn, r.nv
+        keep["w"], keep["phi"], keep["dphi"], keep["psi"], keep["dgphi"] = c(r.w), c(r.phi), c(r.dphi), c(r.psi), c(r.dgphi)
+        d.w, d.phi, d.dphi, d.psi, d.dgphi = _p(keep["w"]), _p(keep["phi"]), _p(keep["dphi"]), _p(keep["psi"]), _p(keep["dgphi"])
+        d.device, d.path = device, path
+        d.rank, d.nranks, d.cell_begin, d.ncells_global = 0, 1, 0, m.ncells
+        self._h = C.c_void_p()
+        self.layout = layout
+        self.n = sp.n_total
+        self.nnz = None
+        _check(lib().gm_create(C.byref(d), C.byref(self._h)))
+        del keep  # the library copied everything
+
+    def close(self):
+        if self._h:
+            lib().gm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_params(self, Pr=1.0, Ra=1.0, n=1.0, reg=1e-3, g=(0.0, 1.0), jac_scaling=1.0):
+        _check(lib().gm_set_params(self._h, C.c_double(Pr), C.c_double(Ra), C.c_double(n), C.c_double(reg),
+                                   C.c_double(g[0]), C.c_double(g[1]), C.c_double(jac_scaling)))
+
+    def pattern(self):
+        nnz = C.c_int64()
+        _check(lib().gm_pattern(self._h, C.byref(nnz)))
+        self.nnz = nnz.value
+        return self.nnz
+
+    def get_pattern(self, index_base=0, with_idx=True):
+        if self.nnz is None:
+            self.pattern()
+        ptr = np.empty(self.n + 1, dtype=np.int64)
+        idx = np.empty(self.nnz, dtype=np.int64) if with_idx else None
+        _check(lib().gm_get_pattern(self._h, _p(ptr), _p(idx), C.c_int32(index_base)))
+        return ptr, idx
+
+    def assemble(self, x, nzval=None, resid=None, flags=None):
+        """Host buffers in/out (numpy float64, C-contiguous)."""
+        if flags is None:
+            flags = (GM_JACOBIAN if nzval is not None else 0) | (GM_RESIDUAL if resid is not None else 0)
+        assert x.dtype == np.float64 and x.flags.c_contiguous and x.size == self.n
+        _check(lib().gm_assemble(self._h, _p(x), _p(nzval), _p(resid), C.c_uint32(flags)))
+
+    def assemble_device(self, d_x, d_nz, d_b, flags, sync=True):
+        """Device pointers (ints)."""
+        _check(lib().gm_assemble_device(self._h, C.c_void_p(d_x), C.c_void_p(d_nz or 0), C.c_void_p(d_b or 0),
+                                        C.c_uint32(flags), C.c_int32(1 if sync else 0)))
+
+    def set_stream(self, stream_ptr):
+        _check(lib().gm_set_stream(self._h, C.c_void_p(stream_ptr)))
+
+    def timing(self):
+        t = gm_times()
+        _check(lib().gm_timing(self._h, C.byref(t)))
+        return {k: getattr(t, k) for k, _ in gm_times._fields_}
+
+    def info(self):
+        n, p, c, b = C.c_int64(), C.c_int32(), C.c_int32(), C.c_int64()
+        _check(lib().gm_info(self._h, C.byref(n), C.byref(p), C.byref(c), C.byref(b)))
+        return dict(n_owned=n.value, active_path=p.value, ncolors=c.value, device_bytes=b.value)
+
+
+def host_register(a: np.ndarray):
+    _check(lib().gm_host_register(_p(a), C.c_int64(a.nbytes)))
+
+
+def host_unregister(a: np.ndarray):
+    _check(lib().gm_host_unregister(_p(a)))

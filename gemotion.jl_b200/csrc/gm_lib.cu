@@ -1,0 +1,420 @@
+// gm_lib.cu -- C ABI of libgemotion_b200.so (see include/gemotion_b200.h).
+// Host orchestration only; the kernels live in gm_pattern.cuh / gm_scatter.cuh / gm_cart.cuh.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "gm_internal.h"
+#include "gm_pattern.cuh"
+#include "gm_scatter.cuh"
+#include "gm_cart.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void gm_set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+
+extern "C" int gm_version(void) { return GM_VERSION; }
+extern "C" const char *gm_last_error(void) { return g_err; }
+
+// ------------------------------------------------------------------------------------------
+// greedy colouring of a generic mesh (host, one-time): no two cells of a colour share a dof
+// ------------------------------------------------------------------------------------------
+static int gm_color_generic(gm_handle *h, const gm_desc *d) {
+  const int nn = h->nn;
+  const int64_t nc = h->ncells;
+  // Cells conflict iff they share a P2 node; the T table numbers every node (free >0, Dirichlet <0),
+  // the U table may have different Dirichlet sets, so use both.
+  auto build = [&](const int32_t *tab, int per, int64_t nfree, int64_t ndiri, std::vector<int64_t> &ptr,
+                   std::vector<int32_t> &adj) {
+    const int64_t nnode = nfree + ndiri;
+    ptr.assign(nnode + 1, 0);
+    auto key = [&](int32_t v) -> int64_t { return v > 0 ? v - 1 : nfree + (-(int64_t)v - 1); };
+    for (int64_t c = 0; c < nc; ++c)
+      for (int l = 0; l < per; ++l) ptr[key(tab[c * per + l]) + 1]++;
+    for (int64_t k = 0; k < nnode; ++k) ptr[k + 1] += ptr[k];
+    adj.resize(ptr[nnode]);
+    std::vector<int64_t> cur(ptr.begin(), ptr.end() - 1);
+    for (int64_t c = 0; c < nc; ++c)
+      for (int l = 0; l < per; ++l) adj[cur[key(tab[c * per + l])]++] = (int32_t)c;
+  };
+  std::vector<int64_t> pt;
+  std::vector<int32_t> at;
+  build(d->cell_dofs_t, nn, d->n_free[2], d->n_diri[2], pt, at);
+  std::vector<int> color(nc, -1);
+  int ncol = 0;
+  std::vector<char> used;
+  for (int64_t c = 0; c < nc; ++c) {
+    used.assign(ncol + 1, 0);
+    for (int l = 0; l < nn; ++l) {
+      const int32_t v = d->cell_dofs_t[c * nn + l];
+      const int64_t k = v > 0 ? v - 1 : d->n_free[2] + (-(int64_t)v - 1);
+      for (int64_t p = pt[k]; p < pt[k + 1]; ++p) {
+        const int cc = color[at[p]];
+        if (cc >= 0) used[cc] = 1;
+      }
+    }
+    int k = 0;
+    while (k < ncol && used[k]) ++k;
+    if (k == ncol) ++ncol;
+    color[c] = k;
+  }
+  h->ncolors = ncol;
+  h->color_ptr.assign(ncol + 1, 0);
+  for (int64_t c = 0; c < nc; ++c) h->color_ptr[color[c] + 1]++;
+  for (int k = 0; k < ncol; ++k) h->color_ptr[k + 1] += h->color_ptr[k];
+  std::vector<int32_t> cells(nc);
+  std::vector<int64_t> cur(h->color_ptr.begin(), h->color_ptr.end() - 1);
+  for (int64_t c = 0; c < nc; ++c) cells[cur[color[c]]++] = (int32_t)c;
+  int rc = gm_dalloc(h, &h->color_cells, nc);
+  if (rc) return rc;
+  GM_CUDA(cudaMemcpy(h->color_cells, cells.data(), sizeof(int32_t) * nc, cudaMemcpyHostToDevice));
+  return GM_OK;
+}
+
+template <typename T>
+static int gm_upload(gm_handle *h, T **dst, const T *src, int64_t count) {
+  int rc = gm_dalloc(h, dst, count);
+  if (rc) return rc;
+  if (count > 0 && src) GM_CUDA(cudaMemcpy(*dst, src, sizeof(T) * (size_t)count, cudaMemcpyHostToDevice));
+  return GM_OK;
+}
+
+extern "C" int gm_create(const gm_desc *d, gm_handle **out) {
+  if (!d || !out) { gm_set_error("gm_create: null argument"); return GM_ERR_ARG; }
+  *out = nullptr;
+  if (d->struct_size != (int32_t)sizeof(gm_desc)) {
+    gm_set_error("gm_create: gm_desc size mismatch (%d vs %d)", d->struct_size, (int)sizeof(gm_desc));
+    return GM_ERR_ARG;
+  }
+  const bool quad = d->cell_type == GM_QUAD;
+  if (!(quad || d->cell_type == GM_TRI)) { gm_set_error("gm_create: unknown cell type %d", d->cell_type); return GM_ERR_ARG; }
+  const int nn = quad ? 9 : 6, nv = quad ? 4 : 3, nq = quad ? 4 : 3;
+  if (d->nn != nn || d->nv != nv || d->nq != nq) {
+    gm_set_error("gm_create: expected nn=%d nv=%d nq=%d (degree-2 measure) for this cell type, got %d %d %d", nn, nv, nq,
+                 d->nn, d->nv, d->nq);
+    return GM_ERR_ARG;
+  }
+  if (d->ncells <= 0 || !d->cell_dofs_u || !d->cell_dofs_p || !d->cell_dofs_t || !d->w || !d->phi || !d->dphi || !d->psi) {
+    gm_set_error("gm_create: missing table");
+    return GM_ERR_ARG;
+  }
+  if (d->cartesian) {
+    if (!quad || (int64_t)d->nx * d->ny != d->ncells || !(d->h[0] > 0) || !(d->h[1] > 0)) {
+      gm_set_error("gm_create: inconsistent Cartesian description");
+      return GM_ERR_ARG;
+    }
+  } else if (!d->coords || !d->cell_vertices || !d->dgphi || d->nverts <= 0) {
+    gm_set_error("gm_create: unstructured mesh needs coords, cell_vertices and dgphi");
+    return GM_ERR_ARG;
+  }
+  if (d->layout != GM_LAYOUT_CSC && d->layout != GM_LAYOUT_CSR) { gm_set_error("gm_create: bad layout"); return GM_ERR_ARG; }
+  const int64_t ntot = d->n_free[0] + d->n_free[1] + d->n_free[2];
+  if (ntot <= 0 || ntot >= (int64_t)INT32_MAX) { gm_set_error("gm_create: n_free out of range"); return GM_ERR_ARG; }
+  for (int f = 0; f < 3; ++f)
+    if (d->n_diri[f] > 0 && !(f == 0 ? d->diri_u : f == 1 ? d->diri_p : d->diri_t)) {
+      gm_set_error("gm_create: Dirichlet values missing for field %d", f);
+      return GM_ERR_ARG;
+    }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || d->device < 0 || d->device >= ndev) {
+    gm_set_error("gm_create: no usable CUDA device (count=%d, requested %d); this library has no CPU path", ndev, d->device);
+    return GM_ERR_CUDA;
+  }
+  GM_CUDA(cudaSetDevice(d->device));
+  cudaDeviceProp prop;
+  GM_CUDA(cudaGetDeviceProperties(&prop, d->device));
+  if (prop.major < 10) {
+    gm_set_error("gm_create: device %d is sm_%d%d; this library is built for sm_100a only", d->device, prop.major, prop.minor);
+    return GM_ERR_CUDA;
+  }
+  gm_handle *h = new (std::nothrow) gm_handle();
+  if (!h) return GM_ERR_OOM;
+  h->d = *d;
+  h->dev = d->device;
+  h->nn = nn; h->nv = nv; h->nq = nq; h->ld = 3 * nn + 3;
+  h->ncells = d->ncells;
+  h->n_total = ntot;
+  h->off[0] = 0; h->off[1] = d->n_free[0]; h->off[2] = d->n_free[0] + d->n_free[1];
+  h->n_diri_total = d->n_diri[0] + d->n_diri[1] + d->n_diri[2];
+  memset(&h->times, 0, sizeof h->times);
+  int rc = GM_OK;
+  auto fail = [&](int code) { gm_destroy(h); return code; };
+#define TRY(x) do { rc = (x); if (rc != GM_OK) return fail(rc); } while (0)
+#define TRYC(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { gm_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); return fail(e__ == cudaErrorMemoryAllocation ? GM_ERR_OOM : GM_ERR_CUDA); } } while (0)
+  TRYC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  h->own_stream = true;
+  for (int k = 0; k < 4; ++k) TRYC(cudaEventCreate(&h->ev[k]));
+  // constants
+  GmConst &c = h->hc;
+  memset(&c, 0, sizeof c);
+  memcpy(c.w, d->w, sizeof(double) * nq);
+  memcpy(c.phi, d->phi, sizeof(double) * nq * nn);
+  memcpy(c.dphi, d->dphi, sizeof(double) * nq * nn * 2);
+  memcpy(c.psi, d->psi, sizeof(double) * nq * 3);
+  if (d->dgphi) memcpy(c.dgphi, d->dgphi, sizeof(double) * nq * nv * 2);
+  c.cartesian = d->cartesian; c.nx = d->nx; c.ny = d->ny; c.hx = d->h[0]; c.hy = d->h[1]; c.layout = d->layout;
+  h->prm = gm_params{1.0, 1.0, 1.0, 1e-3, 0.0, 1.0, 1.0};
+  // tables -> device, combined signed global ids
+  {
+    int32_t *du = nullptr, *dp = nullptr, *dt = nullptr;
+    const int64_t keep = h->device_bytes;
+    TRY(gm_upload(h, &du, d->cell_dofs_u, h->ncells * 2 * nn));
+    TRY(gm_upload(h, &dp, d->cell_dofs_p, h->ncells * 3));
+    TRY(gm_upload(h, &dt, d->cell_dofs_t, h->ncells * nn));
+    TRY(gm_dalloc(h, &h->gdofs, h->ncells * h->ld));
+    k_combine_dofs<<<gm_blocks(h->ncells * h->ld, 256), 256, 0, h->stream>>>(h->ncells, nn, du, dp, dt, h->off[1], h->off[2],
+                                                                             d->n_diri[0], d->n_diri[0] + d->n_diri[1],
+                                                                             h->gdofs);
+    TRYC(cudaStreamSynchronize(h->stream));
+    cudaFree(du); cudaFree(dp); cudaFree(dt);
+    h->device_bytes = keep + (int64_t)sizeof(int32_t) * h->ncells * h->ld;
+  }
+  {
+    std::vector<double> dv((size_t)std::max<int64_t>(h->n_diri_total, 1), 0.0);
+    int64_t o = 0;
+    const double *src[3] = {d->diri_u, d->diri_p, d->diri_t};
+    for (int f = 0; f < 3; ++f) {
+      if (d->n_diri[f] > 0) memcpy(dv.data() + o, src[f], sizeof(double) * d->n_diri[f]);
+      o += d->n_diri[f];
+    }
+    TRY(gm_upload(h, &h->dvals, dv.data(), (int64_t)dv.size()));
+  }
+  if (!d->cartesian) {
+    TRY(gm_upload(h, &h->coords, d->coords, d->nverts * 2));
+    if (d->vertex_index_base == 0) {
+      TRY(gm_upload(h, &h->cellv, d->cell_vertices, h->ncells * nv));
+    } else {
+      std::vector<int32_t> cv((size_t)(h->ncells * nv));
+      for (size_t k = 0; k < cv.size(); ++k) cv[k] = d->cell_vertices[k] - d->vertex_index_base;
+      TRY(gm_upload(h, &h->cellv, cv.data(), (int64_t)cv.size()));
+    }
+    TRY(gm_color_generic(h, d));
+  } else {
+    h->ncolors = 4;
+  }
+  TRY(gm_dalloc(h, &h->d_x, h->n_total));
+  TRY(gm_dalloc(h, &h->d_b, h->n_total));
+  h->active_path = GM_PATH_SCATTER;
+  if (d->cartesian && d->path != GM_PATH_SCATTER) {
+    rc = gm_cart_create(h);  // verifies the tables; keeps the scatter path if they do not fit
+    if (rc != GM_OK && d->path == GM_PATH_CART) return fail(rc);
+  } else if (d->path == GM_PATH_CART) {
+    gm_set_error("gm_create: GM_PATH_CART needs a Cartesian description");
+    return fail(GM_ERR_ARG);
+  }
+#undef TRY
+#undef TRYC
+  // scrub host pointers: the library keeps none
+  h->d.coords = nullptr; h->d.cell_vertices = nullptr; h->d.cell_dofs_u = h->d.cell_dofs_p = h->d.cell_dofs_t = nullptr;
+  h->d.diri_u = h->d.diri_p = h->d.diri_t = nullptr;
+  h->d.w = h->d.phi = h->d.dphi = h->d.psi = h->d.dgphi = nullptr;
+  *out = h;
+  return GM_OK;
+}
+
+extern "C" void gm_destroy(gm_handle *h) {
+  if (!h) return;
+  cudaSetDevice(h->dev);
+  gm_cart_destroy(h);
+  cudaFree(h->gdofs); cudaFree(h->dvals); cudaFree(h->coords); cudaFree(h->cellv);
+  cudaFree(h->ptr); cudaFree(h->idx); cudaFree(h->rank); cudaFree(h->color_cells);
+  cudaFree(h->d_x); cudaFree(h->d_b); cudaFree(h->d_nz);
+  for (int k = 0; k < 4; ++k)
+    if (h->ev[k]) cudaEventDestroy(h->ev[k]);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+extern "C" int gm_set_params(gm_handle *h, double Pr, double Ra, double n, double reg, double gx, double gy,
+                             double jac_scaling) {
+  if (!h) { gm_set_error("gm_set_params: null handle"); return GM_ERR_ARG; }
+  if (!(reg >= 0)) { gm_set_error("gm_set_params: reg must be >= 0"); return GM_ERR_ARG; }
+  h->prm = gm_params{Pr, Ra, n, reg, gx, gy, jac_scaling};
+  return GM_OK;
+}
+
+extern "C" int gm_set_stream(gm_handle *h, void *stream) {
+  if (!h) { gm_set_error("gm_set_stream: null handle"); return GM_ERR_ARG; }
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  h->stream = (cudaStream_t)stream;
+  h->own_stream = false;
+  return GM_OK;
+}
+
+extern "C" int gm_pattern(gm_handle *h, int64_t *nnz) {
+  if (!h) { gm_set_error("gm_pattern: null handle"); return GM_ERR_ARG; }
+  GM_CUDA(cudaSetDevice(h->dev));
+  if (!h->has_pattern) {
+    int rc = gm_build_pattern(h);
+    if (rc) return rc;
+    if (h->active_path == GM_PATH_CART) {
+      rc = gm_cart_after_pattern(h);
+      if (rc) return rc;
+    }
+  }
+  if (nnz) *nnz = h->nnz;
+  return GM_OK;
+}
+
+__global__ void k_widen(const int32_t *__restrict__ s, int64_t *__restrict__ d, int64_t n, int64_t add) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t < n) d[t] = (int64_t)s[t] + add;
+}
+__global__ void k_addbase(const int64_t *__restrict__ s, int64_t *__restrict__ d, int64_t n, int64_t add) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t < n) d[t] = s[t] + add;
+}
+
+extern "C" int gm_get_pattern(gm_handle *h, int64_t *ptr, int64_t *idx, int32_t index_base) {
+  if (!h || !ptr) { gm_set_error("gm_get_pattern: null argument"); return GM_ERR_ARG; }
+  if (!h->has_pattern) { gm_set_error("gm_get_pattern: call gm_pattern first"); return GM_ERR_STATE; }
+  if (idx && !h->idx) { gm_set_error("gm_get_pattern: the index array was released (huge problem)"); return GM_ERR_STATE; }
+  GM_CUDA(cudaSetDevice(h->dev));
+  const int64_t n = h->n_total;
+  const int64_t CH = 1 << 24;
+  int64_t *tmp = nullptr;
+  GM_CUDA(cudaMalloc(&tmp, sizeof(int64_t) * CH));
+  auto chunked = [&](auto launch, int64_t total, int64_t *dst) -> int {
+    for (int64_t o = 0; o < total; o += CH) {
+      const int64_t m = std::min(CH, total - o);
+      launch(o, m);
+      cudaError_t e = cudaMemcpyAsync(dst + o, tmp, sizeof(int64_t) * m, cudaMemcpyDeviceToHost, h->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+      if (e != cudaSuccess) { gm_set_error("gm_get_pattern: %s", cudaGetErrorString(e)); return GM_ERR_CUDA; }
+    }
+    return GM_OK;
+  };
+  int rc = chunked([&](int64_t o, int64_t m) { k_addbase<<<gm_blocks(m, 256), 256, 0, h->stream>>>(h->ptr + o, tmp, m, index_base); }, n + 1, ptr);
+  if (rc == GM_OK && idx)
+    rc = chunked([&](int64_t o, int64_t m) { k_widen<<<gm_blocks(m, 256), 256, 0, h->stream>>>(h->idx + o, tmp, m, index_base); }, h->nnz, idx);
+  cudaFree(tmp);
+  return rc;
+}
+
+static int gm_upload_const(gm_handle *h) {
+  GmConst &c = h->hc;
+  c.Pr = h->prm.Pr; c.Ra = h->prm.Ra; c.n = h->prm.n; c.reg = h->prm.reg;
+  c.gx = h->prm.gx; c.gy = h->prm.gy; c.jac_scaling = h->prm.jac_scaling;
+  GM_CUDA(cudaMemcpyToSymbolAsync(c_gm, &c, sizeof(GmConst), 0, cudaMemcpyHostToDevice, h->stream));
+  return GM_OK;
+}
+
+static int gm_run(gm_handle *h, const double *d_x, double *d_nz, double *d_b, uint32_t flags, int64_t *launches) {
+  if (!h->has_pattern) { gm_set_error("gm_assemble: call gm_pattern first"); return GM_ERR_STATE; }
+  if ((flags & GM_JACOBIAN) && !d_nz) { gm_set_error("gm_assemble: GM_JACOBIAN without nzval"); return GM_ERR_ARG; }
+  if ((flags & GM_RESIDUAL) && !d_b) { gm_set_error("gm_assemble: GM_RESIDUAL without resid"); return GM_ERR_ARG; }
+  if (!(flags & (GM_JACOBIAN | GM_RESIDUAL))) { gm_set_error("gm_assemble: nothing to do"); return GM_ERR_ARG; }
+  int rc = gm_upload_const(h);
+  if (rc) return rc;
+  if (h->active_path == GM_PATH_CART) return gm_cart_run(h, d_x, d_nz, d_b, flags, launches);
+  return gm_launch_scatter(h, d_x, d_nz, d_b, flags, launches);
+}
+
+extern "C" int gm_assemble_device(gm_handle *h, const double *d_x, double *d_nzval, double *d_resid, uint32_t flags,
+                                  int32_t sync) {
+  if (!h || !d_x) { gm_set_error("gm_assemble_device: null argument"); return GM_ERR_ARG; }
+  GM_CUDA(cudaSetDevice(h->dev));
+  int64_t launches = 0;
+  GM_CUDA(cudaEventRecord(h->ev[1], h->stream));
+  int rc = gm_run(h, d_x, d_nzval, d_resid, flags, &launches);
+  if (rc) return rc;
+  GM_CUDA(cudaEventRecord(h->ev[2], h->stream));
+  h->times.launches = launches;
+  h->times.h2d_ms = h->times.d2h_ms = 0;
+  h->times.h2d_bytes = h->times.d2h_bytes = 0;
+  if (sync) {
+    GM_CUDA(cudaStreamSynchronize(h->stream));
+    float ms = 0;
+    GM_CUDA(cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]));
+    h->times.kernel_ms = ms;
+  }
+  return GM_OK;
+}
+
+extern "C" int gm_assemble(gm_handle *h, const double *x, double *nzval, double *resid, uint32_t flags) {
+  if (!h || !x) { gm_set_error("gm_assemble: null argument"); return GM_ERR_ARG; }
+  GM_CUDA(cudaSetDevice(h->dev));
+  if (!h->has_pattern) { gm_set_error("gm_assemble: call gm_pattern first"); return GM_ERR_STATE; }
+  const bool jac = (flags & GM_JACOBIAN) != 0, res = (flags & GM_RESIDUAL) != 0;
+  if (jac && !nzval) { gm_set_error("gm_assemble: GM_JACOBIAN without nzval"); return GM_ERR_ARG; }
+  if (res && !resid) { gm_set_error("gm_assemble: GM_RESIDUAL without resid"); return GM_ERR_ARG; }
+  if (jac && h->d_nz_cap < h->nnz) {
+    cudaFree(h->d_nz);
+    h->d_nz = nullptr;
+    h->d_nz_cap = 0;
+    int rc = gm_dalloc(h, &h->d_nz, h->nnz);
+    if (rc) return rc;
+    h->d_nz_cap = h->nnz;
+  }
+  int64_t launches = 0;
+  GM_CUDA(cudaEventRecord(h->ev[0], h->stream));
+  GM_CUDA(cudaMemcpyAsync(h->d_x, x, sizeof(double) * (size_t)h->n_total, cudaMemcpyHostToDevice, h->stream));
+  GM_CUDA(cudaEventRecord(h->ev[1], h->stream));
+  int rc = gm_run(h, h->d_x, jac ? h->d_nz : nullptr, res ? h->d_b : nullptr, flags, &launches);
+  if (rc) return rc;
+  GM_CUDA(cudaEventRecord(h->ev[2], h->stream));
+  if (jac) GM_CUDA(cudaMemcpyAsync(nzval, h->d_nz, sizeof(double) * (size_t)h->nnz, cudaMemcpyDeviceToHost, h->stream));
+  if (res) GM_CUDA(cudaMemcpyAsync(resid, h->d_b, sizeof(double) * (size_t)h->n_total, cudaMemcpyDeviceToHost, h->stream));
+  GM_CUDA(cudaEventRecord(h->ev[3], h->stream));
+  GM_CUDA(cudaStreamSynchronize(h->stream));
+  float a = 0, b = 0, c = 0;
+  GM_CUDA(cudaEventElapsedTime(&a, h->ev[0], h->ev[1]));
+  GM_CUDA(cudaEventElapsedTime(&b, h->ev[1], h->ev[2]));
+  GM_CUDA(cudaEventElapsedTime(&c, h->ev[2], h->ev[3]));
+  h->times.h2d_ms = a; h->times.kernel_ms = b; h->times.d2h_ms = c;
+  h->times.launches = launches;
+  h->times.h2d_bytes = 8 * h->n_total;
+  h->times.d2h_bytes = (jac ? 8 * h->nnz : 0) + (res ? 8 * h->n_total : 0);
+  if (flags & GM_CHECK_FINITE) {
+    if (res)
+      for (int64_t k = 0; k < h->n_total; ++k)
+        if (!isfinite(resid[k])) { gm_set_error("gm_assemble: non-finite residual entry %lld", (long long)k); return GM_ERR_NONFINITE; }
+  }
+  return GM_OK;
+}
+
+extern "C" int gm_timing(gm_handle *h, gm_times *t) {
+  if (!h || !t) { gm_set_error("gm_timing: null argument"); return GM_ERR_ARG; }
+  *t = h->times;
+  return GM_OK;
+}
+
+extern "C" int gm_info(gm_handle *h, int64_t *n_owned, int32_t *active_path, int32_t *ncolors, int64_t *device_bytes) {
+  if (!h) { gm_set_error("gm_info: null handle"); return GM_ERR_ARG; }
+  if (n_owned) *n_owned = h->n_total;
+  if (active_path) *active_path = h->active_path;
+  if (ncolors) *ncolors = h->ncolors;
+  if (device_bytes) *device_bytes = h->device_bytes;
+  return GM_OK;
+}
+
+extern "C" int gm_host_register(void *ptr, int64_t bytes) {
+  if (!ptr || bytes <= 0) { gm_set_error("gm_host_register: bad argument"); return GM_ERR_ARG; }
+  GM_CUDA(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault));
+  return GM_OK;
+}
+extern "C" int gm_host_unregister(void *ptr) {
+  if (!ptr) { gm_set_error("gm_host_unregister: bad argument"); return GM_ERR_ARG; }
+  GM_CUDA(cudaHostUnregister(ptr));
+  return GM_OK;
+}
+
+extern "C" int gm_nccl_unique_id(void *id128) {
+  (void)id128;
+  gm_set_error("gm_nccl_unique_id: multi-GPU exchange not built in this version");
+  return GM_ERR_NCCL;
+}
+extern "C" int gm_comm_init(gm_handle *h, const void *id128) {
+  (void)h; (void)id128;
+  gm_set_error("gm_comm_init: multi-GPU exchange not built in this version");
+  return GM_ERR_NCCL;
+}

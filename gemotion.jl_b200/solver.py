@@ -1,0 +1,181 @@
+"""Newton driver and `simulate` -- the host loop that CALLS the hot path.
+
+Mirrors the caller side of the reference: `NLSolver(LUSolver(); nlsolver_opts...)`,
+`FESolver`, `solve` (/root/reference/src/Solver.jl:162-195), i.e. NLsolve 4.5.1 `newton_`
+with LineSearches 7.3.0 `BackTracking(order=3, c_1=1e-4, ρ_hi=0.5, ρ_lo=0.1)` (the options
+every example passes, e.g. examples/simple.jl:23-29) and a sparse LU per iteration.  In
+production this loop stays in Julia (NLsolve + UMFPACK); it is restated here only because
+Julia is not in the image, so that end-to-end Newton parity (iteration counts, fields) can
+be tested through the same operator interface the Julia plug-in implements
+(INTEGRATION.md).  The operator `op` must provide
+
+    op.n                                   number of free dofs
+    op.residual_(b, x)                     residual!(b, op, x)
+    op.jacobian_(A, x)                     jacobian!(A, op, x)            A: scipy CSC/CSR
+    op.residual_and_jacobian_(b, A, x)     residual_and_jacobian!(b, A, op, x)
+    op.allocate_jacobian()                 allocate_jacobian(op, x)       (symbolic pattern)
+"""
+from __future__ import annotations
+
+import dataclasses
+import math
+import time
+from typing import Optional
+
+import numpy as np
+import scipy.sparse.linalg as spla
+
+
+@dataclasses.dataclass
+class NLResult:
+    x: np.ndarray
+    iterations: int
+    f_converged: bool
+    x_converged: bool
+    residual_norm: float
+    f_calls: int
+    g_calls: int
+    trace: list
+    t_assembly: float = 0.0
+    t_linsolve: float = 0.0
+
+
+def _nanmin(a, b):
+    return b if math.isnan(a) else (a if math.isnan(b) else min(a, b))
+
+
+def _nanmax(a, b):
+    return b if math.isnan(a) else (a if math.isnan(b) else max(a, b))
+
+
+def backtracking(phi, alpha0, phi0, dphi0, c_1=1e-4, rho_hi=0.5, rho_lo=0.1, iterations=1000, order=3):
+    """LineSearches.BackTracking (v7.3.0) restated: cubic/quadratic interpolation backtracking."""
+    eps = np.finfo(np.float64).eps
+    iterfinitemax = -math.log2(eps)
+    phix_0, phix_1 = phi0, phi0
+    a1, a2 = alpha0, alpha0
+    phix_1 = phi(a1)
+    iterfinite = 0
+    while not math.isfinite(phix_1) and iterfinite < iterfinitemax:
+        iterfinite += 1
+        a1 = a2
+        a2 = a1 / 2
+        phix_1 = phi(a2)
+    it = 0
+    while phix_1 > phi0 + c_1 * a2 * dphi0:
+        it += 1
+        if it > iterations:
+            raise RuntimeError("Linesearch failed to converge, reached maximum iterations %d" % iterations)
+        if order == 2 or it == 1:
+            a_tmp = -(dphi0 * a2 ** 2) / (2 * (phix_1 - phi0 - dphi0 * a2))
+        else:
+            div = 1.0 / (a1 ** 2 * a2 ** 2 * (a2 - a1))
+            a = (a1 ** 2 * (phix_1 - phi0 - dphi0 * a2) - a2 ** 2 * (phix_0 - phi0 - dphi0 * a1)) * div
+            b = (-a1 ** 3 * (phix_1 - phi0 - dphi0 * a2) + a2 ** 3 * (phix_0 - phi0 - dphi0 * a1)) * div
+            if abs(a) <= eps:
+                a_tmp = dphi0 / (2 * b)
+            else:
+                d = max(b * b - 3 * a * dphi0, 0.0)
+                a_tmp = (-b + math.sqrt(d)) / (3 * a)
+        a1 = a2
+        a_tmp = _nanmin(a_tmp, a2 * rho_hi)  # avoid too small reductions
+        a2 = _nanmax(a_tmp, a2 * rho_lo)     # avoid too big reductions
+        phix_0, phix_1 = phix_1, phi(a2)
+    return a2, phix_1
+
+
+def newton(op, x0, ftol=1e-8, xtol=0.0, iterations=1000, linesearch="backtracking",
+           show_trace=False) -> NLResult:
+    """NLsolve.nlsolve(df, x0; method=:newton, linesearch=BackTracking(), ftol, xtol, iterations)."""
+    n = op.n
+    x = np.array(x0, dtype=np.float64, copy=True)
+    f = np.zeros(n)
+    A = op.allocate_jacobian()
+    t_asm = t_lin = 0.0
+    t0 = time.perf_counter()
+    op.residual_and_jacobian_(f, A, x)
+    t_asm += time.perf_counter() - t0
+    f_calls, g_calls = 1, 1
+    if not np.all(np.isfinite(f)):
+        raise FloatingPointError("non-finite residual at the initial guess")
+    xold = np.full(n, np.nan)
+    trace = []
+    it = 0
+    fnorm = float(np.max(np.abs(f))) if n else 0.0
+    x_conv, f_conv = False, fnorm <= ftol
+    trace.append((0, fnorm, float("nan")))
+    if show_trace:
+        print("Iter     f(x) inf-norm    Step 2-norm")
+        print("%6d   %14e   %14e" % trace[-1])
+    stopped = False
+    while not stopped and not (x_conv or f_conv) and it < iterations:
+        it += 1
+        if it > 1:
+            t0 = time.perf_counter()
+            op.jacobian_(A, x)
+            t_asm += time.perf_counter() - t0
+            g_calls += 1
+        t0 = time.perf_counter()
+        lu = spla.splu(A.tocsc() if A.format != "csc" else A)
+        p = -lu.solve(f)
+        t_lin += time.perf_counter() - t0
+        xold[:] = x
+        if linesearch == "static":
+            x = xold + p
+            t0 = time.perf_counter()
+            op.residual_(f, x)
+            t_asm += time.perf_counter() - t0
+            f_calls += 1
+        else:
+            g = A.T @ f
+            phi0 = 0.5 * float(f @ f)
+            dphi0 = float(g @ p)
+            xbase = xold.copy()
+
+            def phi(alpha):
+                nonlocal f_calls, t_asm
+                t1 = time.perf_counter()
+                op.residual_(f, xbase + alpha * p)
+                t_asm += time.perf_counter() - t1
+                f_calls += 1
+                return 0.5 * float(f @ f)
+
+            alpha, _ = backtracking(phi, 1.0, phi0, dphi0)
+            x = xbase + alpha * p
+        fnorm = float(np.max(np.abs(f)))
+        x_conv = float(np.max(np.abs(x - xold))) <= xtol
+        f_conv = fnorm <= ftol
+        stopped = bool(np.any(np.isnan(x)) or np.any(np.isnan(f)))
+        trace.append((it, fnorm, float(np.linalg.norm(x - xold))))
+        if show_trace:
+            print("%6d   %14e   %14e" % trace[-1])
+    return NLResult(x, it, f_conv, x_conv, fnorm, f_calls, g_calls, trace, t_asm, t_lin)
+
+
+# --------------------------------------------------------------------------------------
+# field evaluation helpers used by the parity tests (Nu_bot_avg of examples/study1/study1.jl:223-249)
+# --------------------------------------------------------------------------------------
+def temperature_cell_values(sp, x):
+    """Per-cell nodal T values (free + Dirichlet) [nc, nn]."""
+    oT = sp.offsets[2]
+    d = sp.T.cell_dofs
+    vals = np.where(d > 0, x[oT + np.maximum(d, 1) - 1], sp.T.diri_values[np.maximum(-d, 1) - 1])
+    return vals
+
+
+def nu_bot_avg(sp, x, n_plot=100):
+    """mean over the first n_plot-1 of n_plot equispaced x in [0,1] of -dT/dy(x, 0)
+    (examples/study1/study1.jl:223-249) on a CartesianModel."""
+    from . import fe
+    m = sp.model
+    nx, ny = m.partition
+    hx, hy = m.h
+    Tc = temperature_cell_values(sp, x)
+    xs = np.linspace(0.0, 1.0, n_plot)
+    out = []
+    for X in xs[:-1]:
+        cx = min(int(math.floor((X - m.origin[0]) / hx)), nx - 1)
+        xi = (X - (m.origin[0] + cx * hx)) / hx
+        _, dphi = fe.shape_at(fe.QUAD, xi, 0.0)
+        out.append(-(dphi[:, 1] @ Tc[cx]) / hy)
+    return float(np.sum(out) / len(out))

@@ -1,0 +1,185 @@
+/*
+ * gemotion_b200.h -- C ABI of the B200-native Navier-Stokes-Fourier assembly library
+ * (libgemotion_b200.so, built from gemotion.jl_b200/csrc).
+ *
+ * The reference (lamBOOO/GeMotion.jl) has no FFI of its own: its hot path is entered at
+ *   /root/reference/src/Solver.jl:157      op = FEOperator(res, jac, X, Y)
+ * and executed by Gridap 0.18.9's FEOperatorFromWeakForm / SparseMatrixAssembler through
+ *   allocate_jacobian / jacobian! / residual! / residual_and_jacobian!
+ * which NLsolve calls once per Newton iteration / line-search step (Solver.jl:162-169).
+ * The entry points below are what a Gridap `FEOperator` plug-in binds with `ccall`
+ * (INTEGRATION.md shows the Julia stub).  Each function names the reference interface it
+ * replaces.  Plain pointers and sizes only; no C++ / torch types cross this boundary.
+ *
+ * Conventions
+ *  - Return value: 0 on success, negative gm_status otherwise; text via gm_last_error()
+ *    (thread-local).  No exception, callback or signal crosses the boundary.
+ *  - Ownership: the caller owns every array it passes.  gm_create copies its inputs to the
+ *    device and keeps no host pointer.  Outputs are caller-allocated and written in place.
+ *  - A handle is one assembly context on one CUDA device; calls on one handle must be
+ *    serialised by the caller; distinct handles are independent.
+ *  - There is NO CPU fallback: every entry point fails with GM_ERR_CUDA when no sm_100 device
+ *    is usable.
+ *
+ * Data conventions (Gridap's)
+ *  - cell dof ids are signed, 1-based and FIELD-LOCAL: id>0 free dof, id<0 Dirichlet dof whose
+ *    value is diri_X[-id-1].  Local dof order inside a cell: U: node + nn*comp (all ux, then
+ *    all uy), P: 3, T: nn.  Global free vector x = [U | P | T]  (Solver.jl:104-105,178).
+ *  - gradient convention  G[k][a] = d_k u_a  (Gridap).
+ */
+#ifndef GEMOTION_B200_H
+#define GEMOTION_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GM_VERSION 100 /* 0.1.0 */
+
+enum gm_status {
+  GM_OK = 0,
+  GM_ERR_ARG = -1,      /* bad argument / inconsistent tables */
+  GM_ERR_CUDA = -2,     /* CUDA runtime error or no usable device */
+  GM_ERR_OOM = -3,      /* device or host allocation failed */
+  GM_ERR_STATE = -4,    /* call order (e.g. gm_assemble before gm_pattern) */
+  GM_ERR_NCCL = -5,     /* NCCL error */
+  GM_ERR_NONFINITE = -6 /* non-finite value detected (only with GM_CHECK_FINITE) */
+};
+
+enum gm_cell_type { GM_QUAD = 0, GM_TRI = 1 };
+
+/* Layout of the value array handed back.  Gridap's default matrix is
+ * SparseMatrixCSC{Float64,Int64}; the pattern is structurally symmetric, so the
+ * integer arrays are identical in both layouts and only the value order differs. */
+enum gm_layout { GM_LAYOUT_CSC = 0, GM_LAYOUT_CSR = 1 };
+
+/* gm_assemble flags */
+#define GM_JACOBIAN 1u     /* jacobian!(A, op, x)   */
+#define GM_RESIDUAL 2u     /* residual!(b, op, x)   */
+#define GM_CHECK_FINITE 4u /* scan outputs for NaN/Inf on the device */
+
+/* Numeric kernels */
+enum gm_path {
+  GM_PATH_AUTO = 0,    /* structured if the tables verify as a Cartesian strip mesh, else scatter */
+  GM_PATH_SCATTER = 1, /* colour-ordered atomic-free scatter, any mesh */
+  GM_PATH_CART = 2     /* structured owner-computes row gather, Cartesian quads only */
+};
+
+typedef struct gm_handle gm_handle;
+
+/*
+ * Problem description.  Replaces what Gridap holds inside X, Y, dΩ and the assembler
+ * (Solver.jl:80-109): get_cell_dof_ids per field, get_dirichlet_dof_values, num_free_dofs,
+ * the grid, the cell quadrature and the tabulated reference bases.
+ */
+typedef struct gm_desc {
+  int32_t struct_size; /* = sizeof(gm_desc), for ABI versioning */
+  int32_t cell_type;   /* gm_cell_type */
+  int64_t ncells;
+  int64_t nverts;
+  /* geometry: either Cartesian (cells x-fastest, J = diag(h) exactly like Gridap's
+   * CartesianDiscreteModel) or vertex coordinates + cell->vertex ids */
+  int32_t cartesian;
+  int32_t nx, ny;
+  double origin[2];
+  double h[2];
+  const double *coords;         /* [nverts*2], NULL if cartesian */
+  const int32_t *cell_vertices; /* [ncells*nv], NULL if cartesian */
+  int32_t vertex_index_base;    /* 0 or 1 */
+  int32_t layout;               /* gm_layout of nzval */
+  /* dof tables */
+  const int32_t *cell_dofs_u; /* [ncells*2nn] */
+  const int32_t *cell_dofs_p; /* [ncells*3]   */
+  const int32_t *cell_dofs_t; /* [ncells*nn]  */
+  int64_t n_free[3];          /* U, P, T */
+  int64_t n_diri[3];
+  const double *diri_u, *diri_p, *diri_t;
+  /* reference element + quadrature (Measure(Ω,2), Solver.jl:107-109) */
+  int32_t nq, nn, nv; /* quadrature points, scalar P2 nodes (9|6), geometry nodes (4|3) */
+  const double *w;     /* [nq]       */
+  const double *phi;   /* [nq*nn]    scalar P2 shape values   */
+  const double *dphi;  /* [nq*nn*2]  reference gradients      */
+  const double *psi;   /* [nq*3]     pressure shape values    */
+  const double *dgphi; /* [nq*nv*2]  geometry shape gradients (ignored if cartesian) */
+  /* execution */
+  int32_t device; /* CUDA device ordinal */
+  int32_t path;   /* gm_path */
+  /* multi-GPU row-block partition (one process per GPU).  This rank holds the cells
+   * [cell_begin, cell_end) of a mesh of ncells_global cells; its tables above describe only
+   * those cells but use GLOBAL dof ids.  Single GPU: rank 0 of 1, all cells. */
+  int32_t rank, nranks;
+  int64_t cell_begin, ncells_global;
+} gm_desc;
+
+/* Timings of the last gm_assemble / gm_assemble_device call, milliseconds, CUDA events on the
+ * handle's stream. */
+typedef struct gm_times {
+  double h2d_ms;      /* iterate down */
+  double kernel_ms;   /* all numeric kernels (+ interface exchange) */
+  double d2h_ms;      /* nzval / residual up */
+  double exchange_ms; /* NCCL interface-row reduction inside kernel_ms */
+  int64_t launches;   /* kernels launched by the call */
+  int64_t h2d_bytes, d2h_bytes;
+} gm_times;
+
+int gm_version(void);
+const char *gm_last_error(void);
+
+/* Replaces the construction of the assembler inside FEOperator(res,jac,X,Y) (Solver.jl:157):
+ * copies tables to the device, builds constant tables. */
+int gm_create(const gm_desc *desc, gm_handle **out);
+void gm_destroy(gm_handle *h);
+
+/* Physical parameters captured by the closures at Solver.jl:111-152
+ * (Pr, Ra, n, reg=1e-3, g=(0,1), jac_scaling). */
+int gm_set_params(gm_handle *h, double Pr, double Ra, double n, double reg, double gx, double gy,
+                  double jac_scaling);
+
+/* Replaces allocate_jacobian(op, uh) (the symbolic pass of SparseMatrixAssembler): builds the
+ * sparsity pattern and the cell->nnz index map on the device.  *nnz receives the number of
+ * stored entries (of the rows/columns owned by this rank). */
+int gm_pattern(gm_handle *h, int64_t *nnz);
+
+/* Copies the pattern to the host in Gridap's integer type.  ptr has n_owned+1 entries, idx has
+ * nnz entries; both are written with `index_base` (1 for Julia).  For GM_LAYOUT_CSC these are
+ * (colptr,rowval) of A, for GM_LAYOUT_CSR (rowptr,colind). */
+int gm_get_pattern(gm_handle *h, int64_t *ptr, int64_t *idx, int32_t index_base);
+
+/* Replaces jacobian!(A,op,uh) / residual!(b,op,uh) / residual_and_jacobian!(b,A,op,uh).
+ * x: n_free_total doubles (host).  nzval: nnz doubles or NULL.  resid: n doubles or NULL.
+ * Blocks until the outputs are in host memory. */
+int gm_assemble(gm_handle *h, const double *x, double *nzval, double *resid, uint32_t flags);
+
+/* Same with device-resident buffers (no host copies): used when the caller keeps the matrix on
+ * the GPU, and by bench.py for the HBM-resident figure.  Asynchronous on the handle's stream
+ * unless `sync` != 0. */
+int gm_assemble_device(gm_handle *h, const double *d_x, double *d_nzval, double *d_resid,
+                       uint32_t flags, int32_t sync);
+
+/* Optional: page-lock caller buffers that are reused across Newton iterations (A.nzval, b, x)
+ * so the copies in gm_assemble run at full PCIe speed. */
+int gm_host_register(void *ptr, int64_t bytes);
+int gm_host_unregister(void *ptr);
+
+/* Run the numeric kernels on a caller-provided CUDA stream (cudaStream_t as void*). */
+int gm_set_stream(gm_handle *h, void *stream);
+
+int gm_timing(gm_handle *h, gm_times *t);
+
+/* Introspection used by tests/bench: number of owned rows, which numeric path is active
+ * (gm_path), number of colours of the scatter path, bytes of device memory held. */
+int gm_info(gm_handle *h, int64_t *n_owned, int32_t *active_path, int32_t *ncolors,
+            int64_t *device_bytes);
+
+/* Multi-GPU (one process per GPU).  gm_nccl_unique_id writes 128 bytes on rank 0; the caller
+ * broadcasts them (torch.distributed / MPI / a file) and every rank calls gm_comm_init.  The
+ * interface-row sum of gm_assemble then runs over NCCL. */
+int gm_nccl_unique_id(void *id128);
+int gm_comm_init(gm_handle *h, const void *id128);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEMOTION_B200_H */

@@ -1,0 +1,58 @@
+"""Shared problem set-ups of the reference's configs (BASELINE.json `configs`)."""
+import numpy as np
+
+from _pkg import gm
+
+fe = gm.fe
+
+ALLWALLS = [1, 2, 3, 4, 5, 6, 7, 8]
+SIMPLE = dict(V=ALLWALLS, Ttags=[5, 7, 8, 1, 2], Texpr=[1.0, 0.0, 0.0, 0.5, 0.5])          # examples/simple.jl:32-36
+TURAN = dict(V=ALLWALLS, Ttags=[7, 8, 1, 2, 3, 4], Texpr=[0.0, 1.0, 0.0, 1.0, 0.0, 1.0])   # validation-turan/turan.jl:18-23
+WAVE = dict(V=ALLWALLS, Ttags=[5, 7, 8, 1, 2],
+            Texpr=[lambda x: np.sin(np.pi * x[0]), 0.0, 0.0, 0.0, 0.0])                   # study1/study1.jl:38-43
+KUEHN = dict(V=["all"], Ttags=["inner", "outer"], Texpr=[1.0, 0.0])                       # validation-kuehn/kuehn.jl:47-50
+
+
+def spaces(model, bc):
+    return fe.build_spaces(model, bc["V"], bc["Ttags"], bc["Texpr"])
+
+
+def cart(nx, ny=None, bc=TURAN, domain=(0, 1, 0, 1)):
+    return spaces(fe.CartesianModel(domain, (nx, ny or nx)), bc)
+
+
+def block_scaled_err(a, ref, blocks):
+    """|a-ref| <= tol*max(|ref|, s_B), s_B = max|ref| over the entry's block.
+    Returns max over entries of |a-ref| / max(|ref|, s_B)."""
+    err = 0.0
+    for sel in blocks:
+        if not np.any(sel):
+            continue
+        r = ref[sel]
+        s = np.max(np.abs(r))
+        if s == 0.0:
+            err = max(err, float(np.max(np.abs(a[sel]))))
+            continue
+        err = max(err, float(np.max(np.abs(a[sel] - r) / np.maximum(np.abs(r), s))))
+    return err
+
+
+def field_of_dof(sp):
+    f = np.zeros(sp.n_total, dtype=np.int8)
+    o = sp.offsets
+    f[o[1]:o[2]] = 1
+    f[o[2]:] = 2
+    return f
+
+
+def nz_blocks(sp, ptr, idx):
+    """Boolean masks of the 6 touched (field,field) blocks over the nnz array."""
+    f = field_of_dof(sp)
+    major = np.repeat(np.arange(sp.n_total), np.diff(ptr))
+    fm, fi = f[major], f[idx]
+    return [(fm == a) & (fi == b) for a in range(3) for b in range(3)]
+
+
+def res_blocks(sp):
+    f = field_of_dof(sp)
+    return [f == a for a in range(3)]

@@ -1,0 +1,99 @@
+"""GPU parity: CUDA path (through the C ABI) vs the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): pattern bit-exact; nzval and residual within 1e-12 in the
+block-scaled sense of SURVEY 8a-note.
+"""
+import numpy as np
+import pytest
+
+import cases
+from cases import fe
+from oracle.oracle import Oracle
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12  # north_star: "CSR values and residual within 1e-12 relative in fp64"
+
+PARAMS = [
+    dict(Pr=0.7, Ra=1e3, n=1.0),                       # examples/simple.jl
+    dict(Pr=100.0, Ra=1e5, n=0.6),                     # config 2 (turan-style)
+    dict(Pr=100.0, Ra=1e5, n=1.4, jac_scaling=1e-6),   # config 5 exponent; jac_scaling of validate-matin
+]
+
+
+def _models():
+    yield "cart8_simple", cases.cart(8, bc=cases.SIMPLE)
+    yield "cart13x7_turan", cases.cart(13, 7, bc=cases.TURAN, domain=(0, 2, 0, 1))
+    yield "cart1x1", cases.cart(1, 1, bc=cases.TURAN)
+    yield "cart2x3_wave", cases.cart(2, 3, bc=cases.WAVE)
+    yield "annulus", cases.spaces(fe.annulus_model(nr=4, nt=16, jitter=0.3, seed=1), cases.KUEHN)
+    yield "sqtri", cases.spaces(fe.square_tri_model(6, jitter=0.3, seed=2), cases.TURAN)
+
+
+MODELS = dict(_models())
+
+
+def _check(gm, sp, prm, layout, path, x):
+    orc = Oracle(sp, **prm)
+    optr, oidx = orc.pattern(layout)
+    onz, ob = orc.assemble(x, layout)
+    h = gm.capi.Handle(sp, layout=layout, path=path)
+    try:
+        h.set_params(**prm)
+        nnz = h.pattern()
+        ptr, idx = h.get_pattern()
+        assert nnz == oidx.size
+        assert np.array_equal(ptr, optr) and np.array_equal(idx, oidx), "pattern must be bit-exact"
+        nz = np.full(nnz, np.nan)
+        b = np.full(sp.n_total, np.nan)
+        h.assemble(x, nz, b)
+        e_nz = cases.block_scaled_err(nz, onz, cases.nz_blocks(sp, optr, oidx))
+        e_b = cases.block_scaled_err(b, ob, cases.res_blocks(sp))
+        # stored structural zeros stay exact zeros in the same places
+        assert np.array_equal(onz == 0.0, nz == 0.0)
+        assert e_nz <= TOL and e_b <= TOL, (e_nz, e_b)
+        # residual-only and jacobian-only calls give the same numbers
+        b2 = np.full(sp.n_total, np.nan)
+        h.assemble(x, None, b2)
+        nz2 = np.full(nnz, np.nan)
+        h.assemble(x, nz2, None)
+        assert np.array_equal(b2, b) and np.array_equal(nz2, nz)
+        info = h.info()
+    finally:
+        h.close()
+    return info
+
+
+@pytest.mark.parametrize("name", list(MODELS))
+@pytest.mark.parametrize("pi", range(len(PARAMS)))
+@pytest.mark.parametrize("layout", ["csc", "csr"])
+def test_scatter_path_matches_oracle(gm, gpu_lib, name, pi, layout):
+    sp = MODELS[name]
+    x = fe.splitmix_iterate(sp.n_total, 1234)
+    info = _check(gm, sp, PARAMS[pi], layout, gm.capi.GM_PATH_SCATTER, x)
+    assert info["active_path"] == gm.capi.GM_PATH_SCATTER
+
+
+def test_smooth_iterate_and_zero(gm, gpu_lib):
+    sp = cases.cart(16, bc=cases.TURAN)
+    for x in (fe.smooth_iterate(sp), np.zeros(sp.n_total)):
+        _check(gm, sp, PARAMS[1], "csc", gm.capi.GM_PATH_SCATTER, x)
+
+
+def test_config1_sizes(gm, gpu_lib):
+    """examples/simple.jl: 50x50, nnz = 1,643,902."""
+    sp = cases.cart(50, bc=cases.SIMPLE)
+    assert sp.n_total == 37003
+    info = _check(gm, sp, PARAMS[0], "csc", gm.capi.GM_PATH_AUTO, fe.splitmix_iterate(sp.n_total))
+    assert info["n_owned"] == 37003
+
+
+def test_error_paths(gm, gpu_lib):
+    sp = cases.cart(4)
+    h = gm.capi.Handle(sp)
+    with pytest.raises(gm.capi.GmError):  # assemble before pattern
+        h.assemble(np.zeros(sp.n_total), None, np.zeros(sp.n_total))
+    h.pattern()
+    with pytest.raises(gm.capi.GmError):  # nothing requested
+        h.assemble(np.zeros(sp.n_total), None, None, flags=0)
+    h.close()
