@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py -- Jacobian+residual assembly throughput (Mcells/s, fp64) on B200.
+
+Contract: `python bench.py --gpus N --steps K --warmup W [--impl reference]` prints ONE JSON line.
+
+A "step" is one residual_and_jacobian! assembly (Solver.jl:157/169 hot path) of the whole mesh
+at a fixed synthetic iterate.  Workload (BASELINE.json configs): N=1 -> 2048x2048 Cartesian quads,
+turan BC set, Pr=100, Ra=1e5, n=0.6 (config 4; override with --mesh/--n).  `value` is measured with
+inputs resident in HBM (CUDA events on the launching stream); `e2e` goes through gm_assemble with
+pinned HOST buffers (iterate H2D + nzval/residual D2H inside the timed region).
+`--impl reference`: the CPU oracle (port of the Gridap path; Julia/Gridap cannot run in this image)
+on all host cores on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+METRIC = "Jacobian+residual assembly Mcells/s (fp64)"
+TURAN = dict(V=[1, 2, 3, 4, 5, 6, 7, 8], Ttags=[7, 8, 1, 2, 3, 4], Texpr=[0.0, 1.0, 0.0, 1.0, 0.0, 1.0])
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for k, nme in enumerate(names):
+                    if r[3 + k].lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_problem(N, bc=TURAN):
+    from _pkg import gm
+    model = gm.fe.CartesianModel((0, 1, 0, 1), (N, N))
+    return gm.fe.build_spaces(model, bc["V"], bc["Ttags"], bc["Texpr"])
+
+
+def algorithmic_bytes(sp, nnz):
+    """8*nnz + 8*n (read x) + 8*n (write b) + 4*30*ncells (cell-dof ids); geometry implicit."""
+    return 8 * nnz + 16 * sp.n_total + 4 * 30 * sp.model.ncells
+
+
+def cpu_pass(N, prm, passes, threads=None):
+    """Times the CPU oracle (coloured OpenMP scatter over all host cores) on an N x N sample."""
+    from oracle.oracle import Oracle
+    from _pkg import gm
+    if threads:
+        os.environ["OMP_NUM_THREADS"] = str(threads)
+    sp = build_problem(N)
+    orc = Oracle(sp, **prm)
+    x = gm.fe.splitmix_iterate(sp.n_total, 1234)
+    orc.pattern("csc")
+    nx = N
+    cx, cy = np.tile(np.arange(nx), nx), np.repeat(np.arange(nx), nx)
+    col = (cx & 1) + 2 * (cy & 1)
+    order = np.argsort(col, kind="stable").astype(np.int64)
+    cptr = np.concatenate([[0], np.cumsum(np.bincount(col, minlength=4))]).astype(np.int64)
+    ts = []
+    for _ in range(passes):
+        t0 = time.perf_counter()
+        orc.assemble(x, "csc", colors=(cptr, order))
+        ts.append(time.perf_counter() - t0)
+    return sp.model.ncells, ts, Oracle.num_threads()
+
+
+def run_reference(args, prm):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    N = args.cpu_mesh
+    ncells, ts, thr = cpu_pass(N, prm, args.warmup + args.steps)
+    ts = ts[args.warmup:]
+    ms = 1e3 * float(np.mean(ts))
+    val = ncells / (ms * 1e-3) / 1e6
+    sample = "%dx%d sub-mesh of the workload (same BCs, params, iterate rule), %d passes" % (N, N, args.steps)
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Mcells/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": workload_name(args), "sample": sample},
+           "cpu_baseline": {"value": val, "unit": "Mcells/s", "cores": thr, "kind": "port", "sample": sample},
+           "e2e": {"value": val, "unit": "Mcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def workload_name(args):
+    return "cartesian %dx%d quads, turan BCs, Pr=100 Ra=1e5 n=%g, iterate splitmix64(seed=1234)" % (args.mesh, args.mesh, args.n)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mesh", type=int, default=0, help="cells per side (default 2048 on 1 GPU)")
+    ap.add_argument("--n", type=float, default=0.0, help="power-law index (default 0.6)")
+    ap.add_argument("--layout", default="csc", choices=["csc", "csr"])
+    ap.add_argument("--path", default="auto", choices=["auto", "scatter", "cart"])
+    ap.add_argument("--cpu-mesh", type=int, default=512)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.mesh == 0:
+        args.mesh = 2048
+    if args.n == 0.0:
+        args.n = 0.6
+    prm = dict(Pr=100.0, Ra=1e5, n=args.n)
+    if args.impl == "reference":
+        return run_reference(args, prm)
+
+    import torch
+    from _pkg import gm
+    capi = gm.capi
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the assembly path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    # ---- problem (host tables; in production Gridap supplies them) ----
+    # N>1: replicas of the single-GPU workload until the row-block partition lands (weak scaling).
+    t0 = time.perf_counter()
+    sp = build_problem(args.mesh)
+    x_host = gm.fe.splitmix_iterate(sp.n_total, 1234)
+    t_tables = time.perf_counter() - t0
+    pathid = {"auto": capi.GM_PATH_AUTO, "scatter": capi.GM_PATH_SCATTER, "cart": capi.GM_PATH_CART}[args.path]
+    h = capi.Handle(sp, layout=args.layout, device=local, path=pathid)
+    h.set_params(**prm)
+    t0 = time.perf_counter()
+    nnz = h.pattern()
+    t_pattern = time.perf_counter() - t0
+    info = h.info()
+    stream = torch.cuda.current_stream()
+    h.set_stream(stream.cuda_stream)
+    d_x = torch.from_numpy(x_host).cuda()
+    d_nz = torch.empty(nnz, dtype=torch.float64, device="cuda")
+    d_b = torch.empty(sp.n_total, dtype=torch.float64, device="cuda")
+    flags = capi.GM_JACOBIAN | capi.GM_RESIDUAL
+
+    def step():
+        h.assemble_device(d_x.data_ptr(), d_nz.data_ptr(), d_b.data_ptr(), flags, sync=False)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    launches_per_step = h.timing()["launches"]
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    torch.cuda.synchronize()
+    ev[0].record(stream)
+    for k in range(args.steps):
+        step()
+        ev[k + 1].record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.finish()
+    per = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+    total_ms = ev[0].elapsed_time(ev[args.steps])
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms = total_ms / args.steps
+    ncells_total = sp.model.ncells * world
+    value = ncells_total / (ms * 1e-3) / 1e6
+    # checksum of the result (also the D2H read of the step's result for the record)
+    chk = float(d_b.abs().sum().item())
+
+    # ---- e2e through the C ABI with host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        xh = torch.from_numpy(x_host).pin_memory()
+        nzh = torch.empty(nnz, dtype=torch.float64).pin_memory()
+        bh = torch.empty(sp.n_total, dtype=torch.float64).pin_memory()
+        xn, nzn, bn = xh.numpy(), nzh.numpy(), bh.numpy()
+        h.assemble(xn, nzn, bn)  # warm-up (allocates the device staging buffer)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(args.e2e_steps):
+            t0 = time.perf_counter()
+            h.assemble(xn, nzn, bn)
+            ts.append(time.perf_counter() - t0)
+        tt = h.timing()
+        e_ms = 1e3 * float(np.mean(ts))
+        if world > 1:
+            t = torch.tensor([e_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e_ms = float(t.item())
+        e2e = {"value": ncells_total / (e_ms * 1e-3) / 1e6, "unit": "Mcells/s", "ms_per_step": e_ms,
+               "h2d_bytes_per_step": int(tt["h2d_bytes"]), "d2h_bytes_per_step": int(tt["d2h_bytes"]),
+               "h2d_ms": tt["h2d_ms"], "kernel_ms": tt["kernel_ms"], "d2h_ms": tt["d2h_ms"], "steps": args.e2e_steps,
+               "checksum_match": bool(abs(float(np.abs(bn).sum()) - chk) <= 1e-9 * max(1.0, chk))}
+        del xh, nzh, bh
+
+    if rank != 0:
+        return
+    pk, pk_kind = peaks()
+    balg = algorithmic_bytes(sp, nnz)
+    achieved = balg / (ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
+            "traffic": None, "peak_kind": pk_kind + " (MEASURED_PEAKS.json hbm_gbs, burst copy)",
+            "algorithmic_bytes_per_launch": balg, "bytes_per_cell": balg / sp.model.ncells,
+            "kernel": "whole device step (all numeric kernels of one assembly)"}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            roof["traffic"] = json.load(open(prof)).get(str(args.mesh))
+        except Exception:
+            pass
+    cpu = None
+    if not args.no_cpu:
+        N = args.cpu_mesh
+        ncs, ts, thr = cpu_pass(N, prm, 3)
+        cv = ncs / float(np.mean(ts[1:])) / 1e6
+        cpu = {"value": cv, "unit": "Mcells/s", "cores": thr, "kind": "port",
+               "sample": "%dx%d sub-mesh of the workload, 2 timed passes of the CPU oracle (OpenMP coloured scatter)" % (N, N)}
+    out = {"metric": METRIC, "value": value, "unit": "Mcells/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic",
+           "config": {"workload": workload_name(args), "ncells": sp.model.ncells, "n_free": sp.n_total, "nnz": nnz,
+                      "layout": args.layout, "path": {1: "scatter", 2: "cart"}[info["active_path"]],
+                      "l2": "outputs (%.1f GB) exceed L2 by >100x; no flush needed" % (8 * nnz / 1e9),
+                      "parallelism": "replicas" if world > 1 else "single",
+                      "pattern_s": t_pattern, "tables_s": t_tables, "device_bytes": info["device_bytes"]},
+           "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
+           "clocks": clocks, "ms_per_step_each": per, "checksum_abs_b": chk}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

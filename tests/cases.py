@@ -21,15 +21,18 @@ def cart(nx, ny=None, bc=TURAN, domain=(0, 1, 0, 1)):
     return spaces(fe.CartesianModel(domain, (nx, ny or nx)), bc)
 
 
-def block_scaled_err(a, ref, blocks):
+def block_scaled_err(a, ref, blocks, floor=0.0):
     """|a-ref| <= tol*max(|ref|, s_B), s_B = max|ref| over the entry's block.
-    Returns max over entries of |a-ref| / max(|ref|, s_B)."""
+    Returns max over entries of |a-ref| / max(|ref|, s_B).  `floor` (a fraction of the global
+    max|ref|) bounds s_B from below for iterates whose block is pure cancellation noise (e.g. the
+    pressure residual of a divergence-free smooth iterate is ~1e-17 while its terms are O(1e-2))."""
     err = 0.0
+    gmax = float(np.max(np.abs(ref))) if ref.size else 0.0
     for sel in blocks:
         if not np.any(sel):
             continue
         r = ref[sel]
-        s = np.max(np.abs(r))
+        s = max(np.max(np.abs(r)), floor * gmax)
         if s == 0.0:
             err = max(err, float(np.max(np.abs(a[sel]))))
             continue
