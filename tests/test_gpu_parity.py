@@ -101,3 +101,44 @@ def test_error_paths(gm, gpu_lib):
     with pytest.raises(gm.capi.GmError):  # nothing requested
         h.assemble(np.zeros(sp.n_total), None, None, flags=0)
     h.close()
+
+
+CART_CASES = [
+    ("8x8_simple", 8, 8, cases.SIMPLE), ("13x7_turan", 13, 7, cases.TURAN), ("1x1", 1, 1, cases.TURAN),
+    ("2x3_wave", 2, 3, cases.WAVE), ("20x19_turan", 20, 19, cases.TURAN), ("70x17_simple", 70, 17, cases.SIMPLE),
+    ("130x9_wave", 130, 9, cases.WAVE), ("3x40_turan", 3, 40, cases.TURAN), ("65x24_turan", 65, 24, cases.TURAN),
+]
+
+
+@pytest.mark.parametrize("case", CART_CASES, ids=[c[0] for c in CART_CASES])
+@pytest.mark.parametrize("pi", range(len(PARAMS)))
+@pytest.mark.parametrize("layout", ["csc", "csr"])
+def test_structured_path_matches_oracle(gm, gpu_lib, case, pi, layout):
+    """The owner-computes row-gather kernels (gm_cart.cuh): strips, halo rows, x-chunks, ragged sizes."""
+    _, nx, ny, bc = case
+    sp = cases.cart(nx, ny, bc=bc, domain=(0, 1.5, 0, 1))
+    x = fe.splitmix_iterate(sp.n_total, 1234)
+    info = _check(gm, sp, PARAMS[pi], layout, gm.capi.GM_PATH_CART, x)
+    assert info["active_path"] == gm.capi.GM_PATH_CART
+
+
+def test_structured_equals_scatter_256(gm, gpu_lib):
+    """Config 2 (256x256, n=0.6, Ra=1e5, Pr=100): both CUDA paths agree to 1e-13 (block scaled);
+    too large for the oracle's serial scatter to stay in the seconds range on pytest's budget."""
+    sp = cases.cart(256, bc=cases.TURAN)
+    x = fe.splitmix_iterate(sp.n_total, 1234)
+    out = {}
+    for path in (gm.capi.GM_PATH_SCATTER, gm.capi.GM_PATH_CART):
+        h = gm.capi.Handle(sp, layout="csc", path=path)
+        h.set_params(**PARAMS[1])
+        nnz = h.pattern()
+        assert nnz == 44511759  # SURVEY Appendix B
+        nz, b = np.empty(nnz), np.empty(sp.n_total)
+        h.assemble(x, nz, b)
+        ptr, idx = h.get_pattern()
+        out[path] = (nz, b, ptr, idx)
+        h.close()
+    a, c = out[gm.capi.GM_PATH_SCATTER], out[gm.capi.GM_PATH_CART]
+    assert np.array_equal(a[2], c[2]) and np.array_equal(a[3], c[3])
+    assert cases.block_scaled_err(c[0], a[0], cases.nz_blocks(sp, a[2], a[3])) <= 1e-13
+    assert cases.block_scaled_err(c[1], a[1], cases.res_blocks(sp)) <= 1e-13
