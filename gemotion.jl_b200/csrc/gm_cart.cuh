@@ -30,13 +30,12 @@
 #include "gm_internal.h"
 #include "gm_scatter.cuh"
 
-#define CT_TH 8          // cell rows per strip
 #define CT_XCH 64        // columns per x-chunk
-#define CT_WARPS 12      // 4 cells x 3 thirds per phase
-#define CT_THREADS (CT_WARPS * 32)
 #define CT_MAXCLASS 4096
 
-// shared-memory list slots (doubles).  Node blocks: [list0][list1][list2][3 residual slots]
+// shared-memory list slots (doubles).  Node blocks: [list0][list1][list2][3 residual slots].
+// Every slot is one element longer than its longest list: a list is stored at slot + (global base & 1)
+// so that shared and global addresses are 16-byte aligned together for the TMA bulk copy.
 #define CT_VTX_L1 88
 #define CT_VTX_L2 176
 #define CT_VTX_RES 252
@@ -45,18 +44,15 @@
 #define CT_EDG_L2 104
 #define CT_EDG_RES 150
 #define CT_EDG_BLK 154
-#define CT_CEN_L1 30
-#define CT_CEN_L2 60
-#define CT_CEN_RES 88
-#define CT_CEN_BLK 92
-#define CT_P_RES 54
-#define CT_P_BLK 58
+#define CT_CEN_L1 32
+#define CT_CEN_L2 64
+#define CT_CEN_RES 92
+#define CT_CEN_BLK 96
+#define CT_P_L 20
+#define CT_P_RES 60
+#define CT_P_BLK 64
 #define CT_EVEN_STRIDE (CT_VTX_BLK + CT_EDG_BLK)                  // 410 per cell row
-#define CT_EVEN_SZ (CT_TH * CT_EVEN_STRIDE + CT_VTX_BLK)          // 3536
-#define CT_ODD_STRIDE (CT_EDG_BLK + CT_CEN_BLK)                   // 246
-#define CT_ODD_P0 (CT_TH * CT_ODD_STRIDE + CT_EDG_BLK)            // 2122
-#define CT_ODD_SZ (CT_ODD_P0 + CT_TH * CT_P_BLK)                  // 2586
-#define CT_NCELL (CT_TH + 1)                                      // strip cells + halo
+#define CT_ODD_STRIDE (CT_EDG_BLK + CT_CEN_BLK)                   // 250
 #define CT_UNI 16                                                 // per (cell,q) uniform state
 #define CT_NOD 6                                                  // per (cell,q,node) state
 
@@ -82,6 +78,7 @@ struct gm_cart {
   CartCell *d_cell = nullptr;
   gm_params last_prm;
   bool tab_valid = false;
+  int th = 8;  // cell rows per strip (template parameter of k_cart)
 };
 
 struct CartArgs {
@@ -219,352 +216,7 @@ __global__ void k_ct_visc(int64_t ncells, const int32_t *__restrict__ g, const d
   visc[t * 2 + 1] = 0.5 * (n - 1.0) * pow(gam, 0.5 * (n - 3.0)) * 4.0;
 }
 
-// ------------------------------------------------------------------------------------------
-// main kernel
-// ------------------------------------------------------------------------------------------
-__device__ __constant__ int8_t c_ct_node[3][3] = {{0, 4, 1}, {6, 8, 7}, {2, 5, 3}};  // [iy][ix] -> local node
-
-struct CtSmem {
-  double even[2][CT_EVEN_SZ];
-  double odd[CT_ODD_SZ];
-  double uni[CT_NCELL][4][CT_UNI];
-  double nod[CT_NCELL][4][9][CT_NOD];
-  double val[CT_NCELL][30];
-  int32_t gd[CT_NCELL][30];
-  uint16_t cls[CT_NCELL];
-};
-
-// uniform state slots
-#define U_MU 0
-#define U_G00 1
-#define U_G01 2
-#define U_G10 3
-#define U_G11 4
-#define U_DT0 5
-#define U_DT1 6
-#define U_KAP 7
-#define U_CONV0 8
-#define U_CONV1 9
-#define U_P 10
-#define U_T 11
-#define U_UDT 12
-#define U_DIVU 13
-#define U_U0 14
-#define U_U1 15
-
-template <bool CSR, bool NEWT>
-__global__ void __launch_bounds__(CT_THREADS, 1) k_cart(CartArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  CtSmem &s = *reinterpret_cast<CtSmem *>(smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int y0 = blockIdx.y * CT_TH;
-  const int th = min(CT_TH, a.ny - y0);
-  const bool has_halo = y0 + th < a.ny;
-  const int ncol_cells = th + (has_halo ? 1 : 0);
-  const int x0 = blockIdx.x * CT_XCH, x1 = min(a.nx, x0 + CT_XCH);
-  const int jlo = y0 == 0 ? 0 : 1;
-  const bool jac = (a.flags & GM_JACOBIAN) != 0, res = (a.flags & GM_RESIDUAL) != 0;
-  const CartCell &cc = *a.cc;
-
-  for (int k = tid; k < 2 * CT_EVEN_SZ + CT_ODD_SZ; k += CT_THREADS) s.even[0][k] = 0.0;  // even[2] and odd are contiguous
-
-  // ---- lane role: task type (bottom/mid/top third), cell slot, (major node, minor node)
-  const int tt = warp % 3, slot = warp / 3;
-  const int Mi = lane / 9, mi = lane - Mi * 9;  // major index within the third (= ix), minor node
-  const bool pair_lane = lane < 27;
-  const int ixM = pair_lane ? Mi : 0, iyM = tt;
-  const int M = c_ct_node[iyM][ixM];
-  const int it = CSR ? M : mi, jt = CSR ? mi : M;
-  // register tables of the pair
-  double TA[4], TB[4], TC[4], TD[4], TM[4], TP[4], TK, TUT0, TUT1;
-  {
-    const CartPairTab &t = a.tab[it * 9 + jt];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) { TA[q] = t.TA[q]; TB[q] = t.TB[q]; TC[q] = t.TC[q]; TD[q] = t.TD[q]; TM[q] = t.TM[q]; TP[q] = t.TP[q]; }
-    TK = t.TK; TUT0 = t.TUT0; TUT1 = t.TUT1;
-  }
-  // local dof ids of the three major lists and three minor dofs
-  const int Ld[3] = {M, 9 + M, 21 + M};
-  const int md[3] = {mi, 9 + mi, 21 + mi};
-  // node-type dependent list offsets of the major node
-  const bool mvtx = !(ixM & 1) && !(iyM & 1), mcen = (ixM & 1) && (iyM & 1);
-  const int lo1 = mvtx ? CT_VTX_L1 : (mcen ? CT_CEN_L1 : CT_EDG_L1);
-  const int lo2 = mvtx ? CT_VTX_L2 : (mcen ? CT_CEN_L2 : CT_EDG_L2);
-  // extras: lanes mi<6 of every major: the (U major list a, P minor p) entry [constant]
-  const int ex_a = mi / 3, ex_p = mi % 3;
-  const double ex_val = (pair_lane && mi < 6) ? (CSR ? cc.UP[ex_a * 9 + M][ex_p] : -cc.UP[ex_a * 9 + M][ex_p]) : 0.0;
-  // extras of the mid third: P major lists, two (P list, U minor) entries per lane
-  double pv[2];
-  int pl[2], pd[2];
-#pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const int e = 2 * lane + k;  // 0..53 for lane<27
-    pl[k] = (e / 18) % 3;
-    pd[k] = e % 18;
-    const double up = cc.UP[pd[k]][pl[k]];
-    pv[k] = CSR ? -up : up;  // PU[p,d] = -UP[d,p]
-  }
-  // cached ranks of the current class
-  int cur_cls = -1;
-  uint8_t rk[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-  uint8_t rk_ex = 0xFF, rk_p[2] = {0xFF, 0xFF};
-
-  int eL = 0;  // index of the even buffer holding the LEFT line (right line = 1-eL)
-  __syncthreads();
-
-  const int xs = x0 > 0 ? x0 - 1 : x0;
-  for (int x = xs; x < x1; ++x) {
-    const bool pre = x < x0;  // halo column left of the chunk: only right-line contributions count
-    // =============================== state phase ===============================
-    // S1: dof ids + values of the column's cells
-    for (int k = tid; k < ncol_cells * 30; k += CT_THREADS) {
-      const int cy = k / 30, l = k - cy * 30;
-      const int64_t c = (int64_t)(y0 + cy) * a.nx + x;
-      const int32_t d = a.gdofs[c * 30 + l];
-      s.gd[cy][l] = d;
-      s.val[cy][l] = d > 0 ? a.x[d - 1] : a.dvals[-d - 1];
-      if (l == 0) s.cls[cy] = a.cls[c];
-    }
-    __syncthreads();
-    // S2: fields at the quadrature points: items (cell, q, k<10)
-    for (int k = tid; k < ncol_cells * 40; k += CT_THREADS) {
-      const int cy = k / 40, r = k - cy * 40, q = r / 10, f = r - q * 10;
-      double v = 0;
-      if (f == 9) {
-#pragma unroll
-        for (int m = 0; m < 3; ++m) v += cc.psi[q][m] * s.val[cy][18 + m];
-        s.uni[cy][q][U_P] = v;
-      } else {
-        // f: 0 u0, 1 u1, 2 G00, 3 G01, 4 G10, 5 G11, 6 T, 7 dT0, 8 dT1
-        const double *tab = (f < 2 || f == 6) ? cc.sphi[q] : ((f == 2 || f == 3 || f == 7) ? cc.sdx[q] : cc.sdy[q]);
-        const int vo = (f == 0 || f == 2 || f == 4) ? 0 : ((f == 1 || f == 3 || f == 5) ? 9 : 21);
-#pragma unroll
-        for (int i = 0; i < 9; ++i) v += tab[i] * s.val[cy][vo + i];
-        const int dst = f == 0 ? U_U0 : f == 1 ? U_U1 : f == 2 ? U_G00 : f == 3 ? U_G01 : f == 4 ? U_G10 : f == 5 ? U_G11
-                      : f == 6 ? U_T : f == 7 ? U_DT0 : U_DT1;
-        s.uni[cy][q][dst] = v;
-      }
-    }
-    __syncthreads();
-    // S3: derived uniform state: items (cell, q)
-    for (int k = tid; k < ncol_cells * 4; k += CT_THREADS) {
-      const int cy = k >> 2, q = k & 3;
-      double *u = s.uni[cy][q];
-      double mu = 1.0, kap = 0.0;
-      if (!NEWT) {
-        const int64_t c = (int64_t)(y0 + cy) * a.nx + x;
-        mu = a.visc[(c * 4 + q) * 2];
-        kap = a.visc[(c * 4 + q) * 2 + 1];
-      }
-      u[U_MU] = mu;
-      u[U_KAP] = kap;
-      u[U_CONV0] = u[U_U0] * u[U_G00] + u[U_U1] * u[U_G10];
-      u[U_CONV1] = u[U_U0] * u[U_G01] + u[U_U1] * u[U_G11];
-      u[U_UDT] = u[U_U0] * u[U_DT0] + u[U_U1] * u[U_DT1];
-      u[U_DIVU] = u[U_G00] + u[U_G11];
-    }
-    __syncthreads();
-    // S4: per-node state: items (cell, q, node): S0,S1 raw; S'0,S'1 = js w 2Pr kappa S; c = u.grad phi
-    for (int k = tid; k < ncol_cells * 36; k += CT_THREADS) {
-      const int cy = k / 36, r = k - cy * 36, q = r / 9, i = r - q * 9;
-      const double *u = s.uni[cy][q];
-      const double dx = cc.sdx[q][i], dy = cc.sdy[q][i];
-      const double D01 = 0.5 * (u[U_G01] + u[U_G10]);
-      const double S0 = u[U_G00] * dx + D01 * dy;
-      const double S1 = D01 * dx + u[U_G11] * dy;
-      const double sc = a.js * cc.w[q] * 2.0 * a.Pr * u[U_KAP];
-      double *o = s.nod[cy][q][i];
-      o[0] = S0; o[1] = S1; o[2] = sc * S0; o[3] = sc * S1;
-      o[4] = u[U_U0] * dx + u[U_U1] * dy;
-    }
-    __syncthreads();
-    // S5: residual gather: items (ixn, j', comp); sums the <=2 cells of this column sharing the node
-    if (res) {
-      for (int k = tid; k < 3 * 17 * 3; k += CT_THREADS) {
-        const int ixn = k / 51, r = k - ixn * 51, jp = r / 3, comp = r - jp * 3;
-        if (jp < jlo || jp > 2 * th || (pre && ixn != 2)) continue;
-        double acc = 0;
-        // contributing cells: jp odd -> cell (jp-1)/2 with iy=1; jp even -> cell jp/2 (iy=0) and jp/2-1 (iy=2)
-        for (int side = 0; side < 2; ++side) {
-          int cy, iy;
-          if (jp & 1) { if (side) break; cy = jp >> 1; iy = 1; }
-          else { cy = (jp >> 1) - side; iy = side ? 2 : 0; }
-          if (cy < 0 || cy >= ncol_cells) continue;
-          if (cy == th && iy != 0) continue;  // halo cell: bottom nodes only
-          const int i = c_ct_node[iy][ixn];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const double *u = s.uni[cy][q];
-            const double *nd = s.nod[cy][q][i];
-            const double ph = cc.sphi[q][i], dx = cc.sdx[q][i], dy = cc.sdy[q][i];
-            double v;
-            if (comp == 0) v = 2.0 * a.Pr * u[U_MU] * nd[0] + ph * u[U_CONV0] - dx * u[U_P] - a.RaPr * u[U_T] * a.gx * ph;
-            else if (comp == 1) v = 2.0 * a.Pr * u[U_MU] * nd[1] + ph * u[U_CONV1] - dy * u[U_P] - a.RaPr * u[U_T] * a.gy * ph;
-            else v = u[U_DT0] * dx + u[U_DT1] * dy + u[U_UDT] * ph;
-            acc += cc.w[q] * v;
-          }
-        }
-        double *line = (ixn == 1) ? s.odd : s.even[ixn == 0 ? eL : 1 - eL];
-        const int blk = (ixn == 1) ? (jp >> 1) * CT_ODD_STRIDE + ((jp & 1) ? CT_EDG_BLK + CT_CEN_RES : CT_EDG_RES)
-                                   : (jp >> 1) * CT_EVEN_STRIDE + ((jp & 1) ? CT_VTX_BLK + CT_EDG_RES : CT_VTX_RES);
-        line[blk + comp] += acc;
-      }
-      if (!pre)
-        for (int k = tid; k < th * 3; k += CT_THREADS) {
-          const int cy = k / 3, p = k - cy * 3;
-          double acc = 0;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) acc += cc.wpsi[q][p] * s.uni[cy][q][U_DIVU];
-          s.odd[CT_ODD_P0 + cy * CT_P_BLK + CT_P_RES + p] = acc;
-        }
-    }
-    // =============================== matrix phases ===============================
-    if (jac) {
-      for (int ph = 0; ph < 2; ++ph) {
-        // tasks of this warp in this phase: its regular cell, and (bottom third, slot 0, even phase) the halo cell
-        for (int rep = 0; rep < 2; ++rep) {
-          int cy;
-          if (rep == 0) cy = 2 * slot + ph;
-          else { if (!(ph == 0 && tt == 0 && slot == 0 && has_halo)) break; cy = th; }
-          if (rep == 0 && cy >= th) continue;
-          const int jp = 2 * cy + iyM;  // row index of the major node inside the strip
-          if (jp < jlo || jp > 2 * th) continue;          // list not owned by this strip
-          // class / ranks (warp uniform)
-          const int cl = s.cls[cy];
-          if (cl != cur_cls) {
-            cur_cls = cl;
-            const uint8_t *t = a.ctab + (int64_t)cl * 900;
-            if (pair_lane) {
-#pragma unroll
-              for (int kk = 0; kk < 3; ++kk)
-#pragma unroll
-                for (int ll = 0; ll < 3; ++ll) rk[kk * 3 + ll] = t[md[ll] * 30 + Ld[kk]];
-              rk_ex = mi < 6 ? t[(18 + ex_p) * 30 + Ld[ex_a]] : 0xFF;
-              if (tt == 1) {
-                rk_p[0] = t[pd[0] * 30 + 18 + pl[0]];
-                rk_p[1] = t[pd[1] * 30 + 18 + pl[1]];
-              }
-            }
-          }
-          if (!pair_lane) continue;
-          if (pre && ixM != 2) continue;  // halo column: only the right line is owned
-          // ---- 9 values of the pair
-          double v00 = 0, v01 = 0, v10 = 0, v11 = 0, e = 0, tu0 = 0, tu1 = 0;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const double2 *u2 = reinterpret_cast<const double2 *>(s.uni[cy][q]);
-            const double2 a0 = u2[0], a1 = u2[1], a2 = u2[2], a3 = u2[3];  // (mu,G00) (G01,G10) (G11,dT0) (dT1,kap)
-            const double2 si = *reinterpret_cast<const double2 *>(&s.nod[cy][q][it][0]);
-            const double2 sj = *reinterpret_cast<const double2 *>(&s.nod[cy][q][jt][2]);
-            const double cj = s.nod[cy][q][jt][4];
-            const double mu = a0.x;
-            v00 = fma(mu, TA[q], v00); v11 = fma(mu, TB[q], v11); v01 = fma(mu, TC[q], v01); v10 = fma(mu, TD[q], v10);
-            if (!NEWT) {
-              v00 = fma(si.x, sj.x, v00); v01 = fma(si.x, sj.y, v01); v10 = fma(si.y, sj.x, v10); v11 = fma(si.y, sj.y, v11);
-            }
-            v00 = fma(TM[q], a0.y, v00);  // G00
-            v01 = fma(TM[q], a1.y, v01);  // (a=0,b=1): G[1][0]
-            v10 = fma(TM[q], a1.x, v10);  // (a=1,b=0): G[0][1]
-            v11 = fma(TM[q], a2.x, v11);  // G11
-            e = fma(TP[q], cj, e);
-            tu0 = fma(TM[q], a2.y, tu0);
-            tu1 = fma(TM[q], a3.x, tu1);
-          }
-          v00 += e; v11 += e;
-          const double tt_v = TK + e;
-          // ---- accumulate into the lists of the major node
-          double *line = (ixM == 1) ? s.odd : s.even[ixM == 0 ? eL : 1 - eL];
-          const int row = cy + (iyM >> 1);
-          double *blk = line + ((ixM == 1) ? row * CT_ODD_STRIDE + ((iyM & 1) ? CT_EDG_BLK : 0)
-                                           : row * CT_EVEN_STRIDE + ((iyM & 1) ? CT_VTX_BLK : 0));
-          // value of (major list k, minor dof l) in terms of test/trial
-          //   CSR: major=test (it=M): [k][l] = J[(M,k),(m,l)] ; CSC: major=trial: [k][l] = J[(m,l),(M,k)]
-          double w9[9];
-          if (CSR) {
-            w9[0] = v00; w9[1] = v01; w9[2] = TUT0; w9[3] = v10; w9[4] = v11; w9[5] = TUT1; w9[6] = tu0; w9[7] = tu1; w9[8] = tt_v;
-          } else {
-            w9[0] = v00; w9[1] = v10; w9[2] = tu0; w9[3] = v01; w9[4] = v11; w9[5] = tu1; w9[6] = TUT0; w9[7] = TUT1; w9[8] = tt_v;
-          }
-#pragma unroll
-          for (int kk = 0; kk < 3; ++kk) {
-            double *lst = blk + (kk == 0 ? 0 : (kk == 1 ? lo1 : lo2));
-#pragma unroll
-            for (int ll = 0; ll < 3; ++ll) {
-              const uint8_t r = rk[kk * 3 + ll];
-              if (r != 0xFF) lst[r] += w9[kk * 3 + ll];
-            }
-          }
-          if (rk_ex != 0xFF) (blk + (ex_a == 0 ? 0 : lo1))[rk_ex] += ex_val;
-          if (tt == 1 && cy < th && !pre) {  // P major lists of this cell (complete within the cell)
-            double *pb = s.odd + CT_ODD_P0 + cy * CT_P_BLK;
-            if (rk_p[0] != 0xFF) pb[pl[0] * 18 + rk_p[0]] += pv[0];
-            if (rk_p[1] != 0xFF) pb[pl[1] * 18 + rk_p[1]] += pv[1];
-          }
-        }
-        __syncthreads();
-      }
-    } else {
-      __syncthreads();
-    }
-    // =============================== write-out ===============================
-    if (!pre) {
-      // lists: line 0 (left, even buffer eL), line 1 (mid, odd buffer), line 2 (right) only at the last column
-      const int nlines = (x == a.nx - 1) ? 3 : 2;
-      const int per_line = 17 * 3;
-      const int ntask = nlines * per_line + th * 3;
-      for (int tk = warp; tk < ntask; tk += CT_WARPS) {
-        double *src;
-        int cap;
-        int32_t gdof;
-        int resoff;  // slot holding the residual of this dof
-        double *blk;
-        if (tk < nlines * per_line) {
-          const int ln = tk / per_line, r = tk - ln * per_line, jp = r / 3, k = r - jp * 3;
-          if (jp < jlo || jp > 2 * th) continue;
-          // owning cell / local node of the node (ln, jp)
-          const int cy = jp == 2 * th ? th - 1 : (jp >> 1);
-          const int iy = jp == 2 * th ? 2 : (jp & 1);
-          const int node = c_ct_node[iy][ln];
-          gdof = s.gd[cy][k == 0 ? node : (k == 1 ? 9 + node : 21 + node)];
-          double *line = (ln == 1) ? s.odd : s.even[ln == 0 ? eL : 1 - eL];
-          const bool odd_j = jp & 1;
-          if (ln == 1) {
-            blk = line + (jp >> 1) * CT_ODD_STRIDE + (odd_j ? CT_EDG_BLK : 0);
-            src = blk + (k == 0 ? 0 : (odd_j ? (k == 1 ? CT_CEN_L1 : CT_CEN_L2) : (k == 1 ? CT_EDG_L1 : CT_EDG_L2)));
-            cap = odd_j ? (k == 2 ? 28 : 30) : (k == 2 ? 46 : 52);
-            resoff = odd_j ? CT_CEN_RES : CT_EDG_RES;
-          } else {
-            blk = line + (jp >> 1) * CT_EVEN_STRIDE + (odd_j ? CT_VTX_BLK : 0);
-            src = blk + (k == 0 ? 0 : (odd_j ? (k == 1 ? CT_EDG_L1 : CT_EDG_L2) : (k == 1 ? CT_VTX_L1 : CT_VTX_L2)));
-            cap = odd_j ? (k == 2 ? 46 : 52) : (k == 2 ? 76 : 88);
-            resoff = odd_j ? CT_EDG_RES : CT_VTX_RES;
-          }
-          resoff += k;
-        } else {
-          const int r = tk - nlines * per_line, cy = r / 3, p = r - cy * 3;
-          gdof = s.gd[cy][18 + p];
-          blk = s.odd + CT_ODD_P0 + cy * CT_P_BLK;
-          src = blk + p * 18;
-          cap = 18;
-          resoff = CT_P_RES + p;
-        }
-        if (gdof > 0) {
-          if (jac) {
-            const int64_t base = a.ptr[gdof - 1];
-            const int len = (int)(a.ptr[gdof] - base);
-            for (int k2 = lane; k2 < len; k2 += 32) a.nz[base + k2] = src[k2];
-          }
-          if (res && lane == 0) a.b[gdof - 1] = blk[resoff];
-        }
-        if (jac)
-          for (int k2 = lane; k2 < cap; k2 += 32) src[k2] = 0.0;
-        if (lane == 0) blk[resoff] = 0.0;
-      }
-    }
-    __syncthreads();
-    eL = 1 - eL;  // the right line becomes the next column's left line
-  }
-}
+#include "gm_cart_kernel.cuh"
 
 // ------------------------------------------------------------------------------------------
 // host side
@@ -645,10 +297,10 @@ decided:
   cudaFree(h->rank);
   h->rank = nullptr;
   h->device_bytes -= (int64_t)sizeof(uint16_t) * nc * 900;
-  CB(cudaFuncSetAttribute(k_cart<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtSmem)));
-  CB(cudaFuncSetAttribute(k_cart<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtSmem)));
-  CB(cudaFuncSetAttribute(k_cart<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtSmem)));
-  CB(cudaFuncSetAttribute(k_cart<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CtSmem)));
+  {
+    const char *e = getenv("GM_CART_TH");
+    c->th = (e && atoi(e) == 4) ? 4 : 8;
+  }
 done:
   cudaFree(hash); cudaFree(hash2); cudaFree(cell); cudaFree(cell2); cudaFree(head); cudaFree(cid); cudaFree(rep);
   cudaFree(err); cudaFree(tmp);
@@ -710,6 +362,24 @@ static int gm_cart_tables(gm_handle *h) {
   return GM_OK;
 }
 
+template <int TH, bool CSR, bool NEWT>
+static int gm_cart_launch1(gm_handle *h, const CartArgs &a) {
+  static bool attr_set = false;
+  const size_t sm = sizeof(CtSmem<TH>);
+  if (!attr_set) {
+    GM_CUDA(cudaFuncSetAttribute(k_cart<TH, CSR, NEWT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    attr_set = true;
+  }
+  dim3 grid((a.nx + CT_XCH - 1) / CT_XCH, (a.ny + TH - 1) / TH);
+  k_cart<TH, CSR, NEWT><<<grid, (3 * TH / 2 + 2) * 32, sm, h->stream>>>(a);
+  return GM_OK;
+}
+template <int TH>
+static int gm_cart_launch(gm_handle *h, const CartArgs &a, bool csr, bool newt) {
+  if (csr) return newt ? gm_cart_launch1<TH, true, true>(h, a) : gm_cart_launch1<TH, true, false>(h, a);
+  return newt ? gm_cart_launch1<TH, false, true>(h, a) : gm_cart_launch1<TH, false, false>(h, a);
+}
+
 static int gm_cart_run(gm_handle *h, const double *d_x, double *d_nz, double *d_b, unsigned flags, int64_t *launches) {
   gm_cart *c = (gm_cart *)h->cart;
   int rc = gm_cart_tables(h);
@@ -725,13 +395,9 @@ static int gm_cart_run(gm_handle *h, const double *d_x, double *d_nz, double *d_
     k_ct_visc<<<gm_blocks(h->ncells * 4, 256), 256, 0, h->stream>>>(h->ncells, h->gdofs, h->dvals, d_x, c->d_cell, p.reg, p.n, c->visc);
     ++*launches;
   }
-  dim3 grid((a.nx + CT_XCH - 1) / CT_XCH, (a.ny + CT_TH - 1) / CT_TH);
-  const size_t sm = sizeof(CtSmem);
   const bool csr = h->d.layout == GM_LAYOUT_CSR;
-  if (csr && newt) k_cart<true, true><<<grid, CT_THREADS, sm, h->stream>>>(a);
-  else if (csr) k_cart<true, false><<<grid, CT_THREADS, sm, h->stream>>>(a);
-  else if (newt) k_cart<false, true><<<grid, CT_THREADS, sm, h->stream>>>(a);
-  else k_cart<false, false><<<grid, CT_THREADS, sm, h->stream>>>(a);
+  rc = c->th == 4 ? gm_cart_launch<4>(h, a, csr, newt) : gm_cart_launch<8>(h, a, csr, newt);
+  if (rc) return rc;
   ++*launches;
   GM_CUDA(cudaGetLastError());
   return GM_OK;
