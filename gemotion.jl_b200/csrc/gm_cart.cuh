@@ -389,6 +389,7 @@ static int gm_cart_run(gm_handle *h, const double *d_x, double *d_nz, double *d_
   a.nx = h->d.nx; a.ny = h->d.ny;
   a.gdofs = h->gdofs; a.dvals = h->dvals; a.ptr = h->ptr; a.cls = c->cls; a.ctab = c->ctab; a.visc = c->visc;
   a.tab = c->d_tab; a.cc = c->d_cell; a.x = d_x; a.nz = d_nz; a.b = d_b; a.flags = flags;
+  if (const char *e = getenv("GM_CART_DBG")) a.flags |= (unsigned)atoi(e) << 8;  // experiments only
   a.Pr = p.Pr; a.RaPr = p.Ra * p.Pr; a.gx = p.gx; a.gy = p.gy; a.reg = p.reg; a.n = p.n; a.js = p.jac_scaling;
   const bool newt = p.n == 1.0;
   if (!newt) {

@@ -204,15 +204,69 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
   }
   __syncthreads();
 
-  int eL = 0, eR = 1, eI = 2;  // even buffers: left line, right line, idle (draining / zeroed)
+  int eL = 0, eR = 1, eI = 2;  // even buffers: left line, right line, idle (being written out / zeroed)
+  bool prev_out = false;       // the previous column has completed lists waiting to be written out
+  // write-out of column xw (aux warps): one TMA bulk copy per completed list
+  auto write_out = [&](int xw, int bL, int bR) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const int at = tid - NMW * 32;
+    const int per_line = (2 * TH + 1) * 3;
+    const int nline_tasks = ((xw == a.nx - 1) ? 3 : 2) * per_line;
+    const int wb = xw & 1;
+    const int32_t *gdw = &s.gd[xw % 3][0][0];
+    for (int tk = at; tk < 3 * per_line + th * 3; tk += 64) {
+      if (tk >= nline_tasks && tk < 3 * per_line) continue;
+      const CtDesc d = s.desc[tk];
+      int gi = d.gdidx;
+      if (d.jp != 255) {
+        if (d.jp < jlo || d.jp > 2 * th) continue;
+        if (d.jp == 2 * th) gi += -30 + (c_ct_node[2][d.line] - c_ct_node[0][d.line]);  // top nodes of cell th-1
+      }
+      const int32_t g = gdw[gi];
+      double *line = d.line == 1 ? s.odd[wb] : s.even[d.line == 0 ? bL : bR];
+      if (g > 0) {
+        if (jac) {
+          const long long base = (&s.lbase[wb][0][0])[gi];
+          const int len = (&s.llen[wb][0][0])[gi];
+          const int par = (int)(base & 1);
+          const double *src = line + d.soff + par;  // element k of the list lives at src[k]
+          double *dst = a.nz + base;
+          int k0 = 0, n = len;
+          if (par) { dst[0] = src[0]; k0 = 1; n -= 1; }
+          if (n & 1) { dst[k0 + n - 1] = src[k0 + n - 1]; n -= 1; }
+          if (n > 0) {
+            if (a.flags & 0x100u) {
+            } else if (a.flags & 0x200u) {
+              for (int k2 = 0; k2 < n; k2 += 2) *reinterpret_cast<double2 *>(dst + k0 + k2) = *reinterpret_cast<const double2 *>(src + k0 + k2);
+            } else {
+              ct_bulk_store(dst + k0, src + k0, n * 8);
+            }
+          }
+        }
+        if (res) a.b[g - 1] = line[d.roff];
+      }
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  };
+  auto zero_lines = [&](int be, int bo) {  // aux warps: zero an even and an odd line buffer
+    const int at = tid - NMW * 32;
+    double2 *z0 = reinterpret_cast<double2 *>(s.even[be]);
+    for (int k = at; k < S::EVEN_SZ / 2; k += 64) z0[k] = make_double2(0.0, 0.0);
+    double2 *z1 = reinterpret_cast<double2 *>(s.odd[bo]);
+    for (int k = at; k < S::ODD_SZ / 2; k += 64) z1[k] = make_double2(0.0, 0.0);
+  };
+
   for (int x = xs; x < x1; ++x) {
     const bool pre = x < x0;
     const int sb = x & 1;        // state / value buffer of this column
     const int ob = x & 1;        // odd (mid) line buffer of this column
-    const int32_t(*gd)[30] = s.gd[x % 3];
-    // =============================== state phase ===============================
+    double nv = 0, nvm = 1, nvk = 0; long long nlb = 0; int nll = 0, ncl = 0;
+    int32_t ngd = 0;
+    const bool have_next = x + 1 < x1;
+    if (!is_aux) {
+      // =============================== state phase (matrix warps) ===============================
     // S2: fields at the quadrature points.  item = (cell, q, group): group 0: u0,G00,G10 | 1: u1,G01,G11 | 2: T,dT0,dT1 | 3: p
-    for (int k = tid; k < ncol_cells * 16; k += NT) {
+    for (int k = tid; k < ncol_cells * 16; k += NMW * 32) {
       const int cy = k >> 4, q = (k >> 2) & 3, g = k & 3;
       double *u = s.uni[cy][q];
       if (g == 3) {
@@ -235,9 +289,9 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
         else { u[U_T] = f0; u[U_DT0] = f1; u[U_DT1] = f2; }
       }
     }
-    __syncthreads();
+    asm volatile("bar.sync 2, %0;" ::"n"(NMW * 32) : "memory");  // matrix warps only
     // S4: per-node state; the node-0 item also derives the remaining uniform values
-    for (int k = tid; k < ncol_cells * 36; k += NT) {
+    for (int k = tid; k < ncol_cells * 36; k += NMW * 32) {
       const int cy = k / 36, r = k - cy * 36, q = r / 9, i = r - q * 9;
       double *u = s.uni[cy][q];
       const double u0 = u[U_U0], u1 = u[U_U1], G00 = u[U_G00], G01 = u[U_G01], G10 = u[U_G10], G11 = u[U_G11];
@@ -256,16 +310,109 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
         u[U_DIVU] = G00 + G11;
       }
     }
-    __syncthreads();
-    // ---- issue the global loads of the next columns (parked in registers over the matrix phases)
-    double nv = 0, nvm = 1, nvk = 0; long long nlb = 0; int nll = 0, ncl = 0;
-    int32_t ngd = 0;
-    const bool have_next = x + 1 < x1;
-    if (have_next) {
-      fetch_col(x + 1, nv, nlb, nll, nvm, nvk, ncl);
-      if (x + 2 < x1 && pf_on) ngd = load_gd(x + 2);
+    } else if (prev_out) {
+      // ============ write-out of the previous column (aux warps), overlapped with the state phase ============
+      write_out(x - 1, eI, eR);   // previous left line is this column's idle buffer; its right line (last column only) never gets here
     }
-    if (is_aux) {
+    __syncthreads();  // B: state of column x ready
+    if (!is_aux) {
+      // ---- issue the global loads of the next columns (parked in registers over the matrix phases)
+            if (have_next) {
+        fetch_col(x + 1, nv, nlb, nll, nvm, nvk, ncl);
+        if (x + 2 < x1 && pf_on) ngd = load_gd(x + 2);
+      }
+      if (jac) {
+        // =============================== matrix phases ===============================
+        for (int ph = 0; ph < 2; ++ph) {
+          for (int rep = 0; rep < 2; ++rep) {
+            int cy;
+            if (rep == 0) cy = 2 * slot + ph;
+            else { if (!(ph == 0 && tt == 0 && slot == 0 && has_halo)) break; cy = th; }
+            if (rep == 0 && cy >= th) continue;
+            const int jp = 2 * cy + iyM;
+            if (jp < jlo || jp > 2 * th) continue;
+            const int cl = s.cls[sb][cy];
+            if (cl != cur_cls) {
+              cur_cls = cl;
+              const uint8_t *t = a.ctab + (int64_t)cl * 900;
+              if (lane < 27) {
+  #pragma unroll
+                for (int kk = 0; kk < 3; ++kk)
+  #pragma unroll
+                  for (int ll = 0; ll < 3; ++ll) rk[kk * 3 + ll] = t[md[ll] * 30 + Ld[kk]];
+                rk_ex = mi < 6 ? t[(18 + ex_p) * 30 + Ld[ex_a]] : 0xFF;
+                if (tt == 1) {
+                  rk_p[0] = t[pd[0] * 30 + 18 + pl[0]];
+                  rk_p[1] = t[pd[1] * 30 + 18 + pl[1]];
+                }
+              }
+            }
+            if (!pair_lane) continue;
+            if (pre && ixM != 2) continue;
+            double v00 = 0, v01 = 0, v10 = 0, v11 = 0, e = 0, tu0 = 0, tu1 = 0;
+  #pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const double2 *u2 = reinterpret_cast<const double2 *>(s.uni[cy][q]);
+              const double2 a0 = u2[0], a1 = u2[1], a2 = u2[2], a3 = u2[3];  // (mu,G00) (G01,G10) (G11,dT0) (dT1,kap)
+              const double2 si = *reinterpret_cast<const double2 *>(&s.nod[cy][q][it][0]);
+              const double2 sj = *reinterpret_cast<const double2 *>(&s.nod[cy][q][jt][2]);
+              const double cj = s.nod[cy][q][jt][4];
+              const double mu = a0.x;
+              v00 = fma(mu, TA[q], v00); v11 = fma(mu, TB[q], v11); v01 = fma(mu, TC[q], v01); v10 = fma(mu, TD[q], v10);
+              if (!NEWT) {
+                v00 = fma(si.x, sj.x, v00); v01 = fma(si.x, sj.y, v01); v10 = fma(si.y, sj.x, v10); v11 = fma(si.y, sj.y, v11);
+              }
+              v00 = fma(TM[q], a0.y, v00);
+              v01 = fma(TM[q], a1.y, v01);  // (a=0,b=1): G[1][0]
+              v10 = fma(TM[q], a1.x, v10);  // (a=1,b=0): G[0][1]
+              v11 = fma(TM[q], a2.x, v11);
+              e = fma(TP[q], cj, e);
+              tu0 = fma(TM[q], a2.y, tu0);
+              tu1 = fma(TM[q], a3.x, tu1);
+            }
+            v00 += e; v11 += e;
+            const double tt_v = TK + e;
+            double *line = (ixM == 1) ? s.odd[ob] : s.even[ixM == 0 ? eL : eR];
+            const int row = cy + (iyM >> 1);
+            double *blk = line + ((ixM == 1) ? row * CT_ODD_STRIDE + ((iyM & 1) ? CT_EDG_BLK : 0)
+                                             : row * CT_EVEN_STRIDE + ((iyM & 1) ? CT_VTX_BLK : 0));
+            double w9[9];
+            if (CSR) {
+              w9[0] = v00; w9[1] = v01; w9[2] = TUT0; w9[3] = v10; w9[4] = v11; w9[5] = TUT1; w9[6] = tu0; w9[7] = tu1; w9[8] = tt_v;
+            } else {
+              w9[0] = v00; w9[1] = v10; w9[2] = tu0; w9[3] = v01; w9[4] = v11; w9[5] = tu1; w9[6] = TUT0; w9[7] = TUT1; w9[8] = tt_v;
+            }
+            // list k starts at slot + parity of its global base, so that shared and global addresses
+            // are 16-byte aligned together (TMA bulk copy)
+            int par[3];
+  #pragma unroll
+            for (int kk = 0; kk < 3; ++kk) par[kk] = (int)(s.lbase[sb][cy][Ld[kk]] & 1);
+  #pragma unroll
+            for (int kk = 0; kk < 3; ++kk) {
+              double *lst = blk + (kk == 0 ? 0 : (kk == 1 ? lo1 : lo2)) + par[kk];
+  #pragma unroll
+              for (int ll = 0; ll < 3; ++ll) {
+                const uint8_t r = rk[kk * 3 + ll];
+                if (r != 0xFF) lst[r] += w9[kk * 3 + ll];
+              }
+            }
+            if (rk_ex != 0xFF) (blk + (ex_a == 0 ? par[0] : lo1 + par[1]))[rk_ex] += ex_val;
+            if (tt == 1 && cy < th && !pre) {
+              double *pb = s.odd[ob] + S::ODD_P0 + cy * CT_P_BLK;
+  #pragma unroll
+              for (int k = 0; k < 2; ++k)
+                if (rk_p[k] != 0xFF) pb[pl[k] * CT_P_L + (int)(s.lbase[sb][cy][18 + pl[k]] & 1) + rk_p[k]] += pv[k];
+            }
+          }
+          if (ph == 0) asm volatile("bar.sync 1, %0;" ::"n"(NMW * 32) : "memory");  // matrix warps only
+        }
+      }
+      // park the prefetched column in shared memory
+      if (have_next) {
+        store_col(x + 1, nv, nlb, nll, nvm, nvk, ncl);
+        if (x + 2 < x1 && pf_on) s.gd[(x + 2) % 3][pf_cy][pf_l] = ngd;
+      }
+    } else {
       // =========================== residual gather (aux warps) ===========================
       if (res) {
         const int at = tid - NMW * 32;
@@ -306,150 +453,22 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
             s.odd[ob][S::ODD_P0 + cy * CT_P_BLK + CT_P_RES + p] = acc;
           }
       }
-    } else if (jac) {
-      // =============================== matrix phases ===============================
-      for (int ph = 0; ph < 2; ++ph) {
-        for (int rep = 0; rep < 2; ++rep) {
-          int cy;
-          if (rep == 0) cy = 2 * slot + ph;
-          else { if (!(ph == 0 && tt == 0 && slot == 0 && has_halo)) break; cy = th; }
-          if (rep == 0 && cy >= th) continue;
-          const int jp = 2 * cy + iyM;
-          if (jp < jlo || jp > 2 * th) continue;
-          const int cl = s.cls[sb][cy];
-          if (cl != cur_cls) {
-            cur_cls = cl;
-            const uint8_t *t = a.ctab + (int64_t)cl * 900;
-            if (lane < 27) {
-#pragma unroll
-              for (int kk = 0; kk < 3; ++kk)
-#pragma unroll
-                for (int ll = 0; ll < 3; ++ll) rk[kk * 3 + ll] = t[md[ll] * 30 + Ld[kk]];
-              rk_ex = mi < 6 ? t[(18 + ex_p) * 30 + Ld[ex_a]] : 0xFF;
-              if (tt == 1) {
-                rk_p[0] = t[pd[0] * 30 + 18 + pl[0]];
-                rk_p[1] = t[pd[1] * 30 + 18 + pl[1]];
-              }
-            }
-          }
-          if (!pair_lane) continue;
-          if (pre && ixM != 2) continue;
-          double v00 = 0, v01 = 0, v10 = 0, v11 = 0, e = 0, tu0 = 0, tu1 = 0;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const double2 *u2 = reinterpret_cast<const double2 *>(s.uni[cy][q]);
-            const double2 a0 = u2[0], a1 = u2[1], a2 = u2[2], a3 = u2[3];  // (mu,G00) (G01,G10) (G11,dT0) (dT1,kap)
-            const double2 si = *reinterpret_cast<const double2 *>(&s.nod[cy][q][it][0]);
-            const double2 sj = *reinterpret_cast<const double2 *>(&s.nod[cy][q][jt][2]);
-            const double cj = s.nod[cy][q][jt][4];
-            const double mu = a0.x;
-            v00 = fma(mu, TA[q], v00); v11 = fma(mu, TB[q], v11); v01 = fma(mu, TC[q], v01); v10 = fma(mu, TD[q], v10);
-            if (!NEWT) {
-              v00 = fma(si.x, sj.x, v00); v01 = fma(si.x, sj.y, v01); v10 = fma(si.y, sj.x, v10); v11 = fma(si.y, sj.y, v11);
-            }
-            v00 = fma(TM[q], a0.y, v00);
-            v01 = fma(TM[q], a1.y, v01);  // (a=0,b=1): G[1][0]
-            v10 = fma(TM[q], a1.x, v10);  // (a=1,b=0): G[0][1]
-            v11 = fma(TM[q], a2.x, v11);
-            e = fma(TP[q], cj, e);
-            tu0 = fma(TM[q], a2.y, tu0);
-            tu1 = fma(TM[q], a3.x, tu1);
-          }
-          v00 += e; v11 += e;
-          const double tt_v = TK + e;
-          double *line = (ixM == 1) ? s.odd[ob] : s.even[ixM == 0 ? eL : eR];
-          const int row = cy + (iyM >> 1);
-          double *blk = line + ((ixM == 1) ? row * CT_ODD_STRIDE + ((iyM & 1) ? CT_EDG_BLK : 0)
-                                           : row * CT_EVEN_STRIDE + ((iyM & 1) ? CT_VTX_BLK : 0));
-          double w9[9];
-          if (CSR) {
-            w9[0] = v00; w9[1] = v01; w9[2] = TUT0; w9[3] = v10; w9[4] = v11; w9[5] = TUT1; w9[6] = tu0; w9[7] = tu1; w9[8] = tt_v;
-          } else {
-            w9[0] = v00; w9[1] = v10; w9[2] = tu0; w9[3] = v01; w9[4] = v11; w9[5] = tu1; w9[6] = TUT0; w9[7] = TUT1; w9[8] = tt_v;
-          }
-          // list k starts at slot + parity of its global base, so that shared and global addresses
-          // are 16-byte aligned together (TMA bulk copy)
-          int par[3];
-#pragma unroll
-          for (int kk = 0; kk < 3; ++kk) par[kk] = (int)(s.lbase[sb][cy][Ld[kk]] & 1);
-#pragma unroll
-          for (int kk = 0; kk < 3; ++kk) {
-            double *lst = blk + (kk == 0 ? 0 : (kk == 1 ? lo1 : lo2)) + par[kk];
-#pragma unroll
-            for (int ll = 0; ll < 3; ++ll) {
-              const uint8_t r = rk[kk * 3 + ll];
-              if (r != 0xFF) lst[r] += w9[kk * 3 + ll];
-            }
-          }
-          if (rk_ex != 0xFF) (blk + (ex_a == 0 ? par[0] : lo1 + par[1]))[rk_ex] += ex_val;
-          if (tt == 1 && cy < th && !pre) {
-            double *pb = s.odd[ob] + S::ODD_P0 + cy * CT_P_BLK;
-#pragma unroll
-            for (int k = 0; k < 2; ++k)
-              if (rk_p[k] != 0xFF) pb[pl[k] * CT_P_L + (int)(s.lbase[sb][cy][18 + pl[k]] & 1) + rk_p[k]] += pv[k];
-          }
-        }
-        if (ph == 0) asm volatile("bar.sync 1, %0;" ::"n"(NMW * 32) : "memory");  // matrix warps only
-      }
-    }
-    __syncthreads();
-    // =============================== write-out (aux warps) ===============================
-    if (is_aux) {
-      // copies issued one column ago have had a whole column to drain
+      // the copies issued at the top of this iteration have drained by now: recycle their buffers
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      if (!pre) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        const int at = tid - NMW * 32;
-        const int per_line = (2 * TH + 1) * 3;
-        const int nline_tasks = ((x == a.nx - 1) ? 3 : 2) * per_line;
-        for (int tk = at; tk < 3 * per_line + th * 3; tk += 64) {
-          if (tk >= nline_tasks && tk < 3 * per_line) continue;
-          const CtDesc d = s.desc[tk];
-          int gi = d.gdidx;
-          if (d.jp != 255) {
-            if (d.jp < jlo || d.jp > 2 * th) continue;
-            if (d.jp == 2 * th) gi += -30 + (c_ct_node[2][d.line] - c_ct_node[0][d.line]);  // top nodes of cell th-1
-          }
-          const int32_t g = (&gd[0][0])[gi];
-          double *line = d.line == 1 ? s.odd[ob] : s.even[d.line == 0 ? eL : eR];
-          if (g > 0) {
-            if (jac) {
-              const long long base = (&s.lbase[sb][0][0])[gi];
-              const int len = (&s.llen[sb][0][0])[gi];
-              const int par = (int)(base & 1);
-              const double *src = line + d.soff + par;  // element k of the list lives at src[k]
-              double *dst = a.nz + base;
-              int k0 = 0, n = len;
-              if (par) { dst[0] = src[0]; k0 = 1; n -= 1; }
-              if (n & 1) { dst[k0 + n - 1] = src[k0 + n - 1]; n -= 1; }
-              if (n > 0) ct_bulk_store(dst + k0, src + k0, n * 8);
-            }
-            if (res) a.b[g - 1] = line[d.roff];
-          }
-        }
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      }
+      if (prev_out) zero_lines(eI, ob ^ 1);
     }
-    // park the prefetched column in shared memory
-    if (have_next) {
-      store_col(x + 1, nv, nlb, nll, nvm, nvk, ncl);
-      if (x + 2 < x1 && pf_on) s.gd[(x + 2) % 3][pf_cy][pf_l] = ngd;
-    }
-    __syncthreads();
-    // zero the buffers written out one column ago (their copies were waited for above)
-    {
-      double2 *z0 = reinterpret_cast<double2 *>(s.even[eI]);
-      for (int k = tid; k < S::EVEN_SZ / 2; k += NT) z0[k] = make_double2(0.0, 0.0);
-      double2 *z1 = reinterpret_cast<double2 *>(s.odd[ob ^ 1]);
-      for (int k = tid; k < S::ODD_SZ / 2; k += NT) z1[k] = make_double2(0.0, 0.0);
-    }
-    // rotate: right -> left, idle (now zero) -> right, left -> idle (draining)
+    __syncthreads();  // A: lists of column x complete, recycled buffers zero
+    prev_out = !pre;
     if (pre) {
-      const int t = eL; eL = eR; eR = t;  // nothing was written out: old left is still all zero
+      const int t = eL; eL = eR; eR = t;  // nothing to write out: the old left line is still all zero
     } else {
       const int t = eL; eL = eR; eR = eI; eI = t;
     }
-    __syncthreads();
+  }
+  // last column of the chunk: write it out (including the right line at the mesh boundary)
+  if (is_aux && prev_out) {
+    // after the final rotation: previous left = eI, previous right = eL
+    write_out(x1 - 1, eI, eL);
   }
   if (is_aux) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
