@@ -34,25 +34,26 @@
 #define CT_MAXCLASS 4096
 
 // shared-memory list slots (doubles).  Node blocks: [list0][list1][list2][3 residual slots].
-// Every slot is one element longer than its longest list: a list is stored at slot + (global base & 1)
-// so that shared and global addresses are 16-byte aligned together for the TMA bulk copy.
-#define CT_VTX_L1 88
-#define CT_VTX_L2 176
-#define CT_VTX_RES 252
-#define CT_VTX_BLK 256
-#define CT_EDG_L1 52
-#define CT_EDG_L2 104
-#define CT_EDG_RES 150
-#define CT_EDG_BLK 154
+// Every slot is two elements longer than its longest list: a list is stored at slot + (global base & 1)
+// so that shared and global addresses are 16-byte aligned together for the TMA bulk copy, and element
+// cap-2(+parity) is a trash element that absorbs the entries of Dirichlet minors without a branch.
+#define CT_VTX_L1 90
+#define CT_VTX_L2 180
+#define CT_VTX_RES 258
+#define CT_VTX_BLK 262
+#define CT_EDG_L1 54
+#define CT_EDG_L2 108
+#define CT_EDG_RES 156
+#define CT_EDG_BLK 160
 #define CT_CEN_L1 32
 #define CT_CEN_L2 64
-#define CT_CEN_RES 92
-#define CT_CEN_BLK 96
+#define CT_CEN_RES 94
+#define CT_CEN_BLK 98
 #define CT_P_L 20
 #define CT_P_RES 60
 #define CT_P_BLK 64
-#define CT_EVEN_STRIDE (CT_VTX_BLK + CT_EDG_BLK)                  // 410 per cell row
-#define CT_ODD_STRIDE (CT_EDG_BLK + CT_CEN_BLK)                   // 250
+#define CT_EVEN_STRIDE (CT_VTX_BLK + CT_EDG_BLK)                  // 422 per cell row
+#define CT_ODD_STRIDE (CT_EDG_BLK + CT_CEN_BLK)                   // 258
 #define CT_UNI 16                                                 // per (cell,q) uniform state
 #define CT_NOD 6                                                  // per (cell,q,node) state
 
@@ -299,7 +300,7 @@ decided:
   h->device_bytes -= (int64_t)sizeof(uint16_t) * nc * 900;
   {
     const char *e = getenv("GM_CART_TH");
-    c->th = (e && atoi(e) == 4) ? 4 : 8;
+    c->th = (e && atoi(e) == 8) ? 8 : 4;  // TH=4 (2 CTAs/SM) measured faster than TH=8 (1 CTA/SM)
   }
 done:
   cudaFree(hash); cudaFree(hash2); cudaFree(cell); cudaFree(cell2); cudaFree(head); cudaFree(cid); cudaFree(rep);

@@ -1,15 +1,18 @@
 // gm_cart_kernel.cuh -- the sweep kernel of the structured path (see gm_cart.cuh for the design).
 //
 // CTA = 3*TH/2 matrix warps + 2 aux warps.  Per column x of the strip:
-//   all warps : state phase (fields at the quadrature points, S, u.grad(phi)) for the TH(+1 halo) cells
-//   matrix    : two colour phases (even / odd cell rows); lane = (major node, minor node) pair,
-//               pair tables in registers, 9 values accumulated into the shared-memory lists
-//   aux       : residual gather for the column (concurrently with the matrix phases), then the
-//               write-out: one TMA bulk copy (cp.async.bulk shared->global) per completed list
-//   all warps : zero the line buffers whose copies have drained (three even / two odd line
-//               buffers rotate so a copy has a full column of time to drain)
-// Global loads of the next column (dof ids two columns ahead, iterate / list bases / viscosity
-// one column ahead) are issued before the matrix phases and parked in registers.
+//   matrix : state phase (fields at the quadrature points, S, u.grad(phi)) for the TH(+1 halo)
+//            cells, then two colour phases (even / odd cell rows); lane = (major node, minor node)
+//            pair with its reference-element tables in registers; 9 values (+ constant P-block
+//            entries) are accumulated into the shared-memory lists without branches (entries of
+//            Dirichlet minors go to a trash element at the end of each slot)
+//   aux    : write-out of the PREVIOUS column -- one TMA bulk copy (cp.async.bulk shared->global)
+//            per completed list -- overlapped with the matrix warps' state phase, then the
+//            residual gather of this column overlapped with the matrix phases, then recycling
+//            (zeroing) of the line buffers whose copies have drained
+// Three even-line and two odd-line buffers rotate.  Global loads of the next column (dof ids two
+// columns ahead, iterate / list bases / viscosity one column ahead) are issued before the matrix
+// phases and parked in registers.
 #pragma once
 
 __device__ __constant__ int8_t c_ct_node[3][3] = {{0, 4, 1}, {6, 8, 7}, {2, 5, 3}};  // [iy][ix] -> local node
@@ -28,13 +31,15 @@ struct CtSmem {
   static constexpr int EVEN_SZ = TH * CT_EVEN_STRIDE + CT_VTX_BLK;
   static constexpr int ODD_P0 = TH * CT_ODD_STRIDE + CT_EDG_BLK;
   static constexpr int ODD_SZ = ODD_P0 + TH * CT_P_BLK;
-  static constexpr int NDESC = 3 * (2 * TH + 1) * 3 + TH * 3;
+  static constexpr int NNODE = 3 * (2 * TH + 1);
+  static constexpr int NDESC = NNODE * 3 + TH * 3;
   double even[3][EVEN_SZ];
   double odd[2][ODD_SZ];
   double uni[NC][4][CT_UNI];
   double nod[NC][4][9][CT_NOD];
   double val[2][NC][30];
   double visc[2][NC][4][2];
+  double tphi[4][9], tdx[4][9], tdy[4][9], tw[4], twpsi[4][3], tpsi[4][3];
   long long lbase[2][NC][30];
   int32_t llen[2][NC][30];
   int32_t gd[3][NC][30];
@@ -65,16 +70,22 @@ __device__ __forceinline__ void ct_bulk_store(double *gdst, const double *ssrc, 
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(sa), "r"(bytes) : "memory");
 }
 
+__device__ __forceinline__ void ct_rmw(char *base, int off, double v) {
+  double *p = reinterpret_cast<double *>(base + off);
+  *p += v;
+}
+
 template <int TH, bool CSR, bool NEWT>
 __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_cart(CartArgs a) {
   using S = CtSmem<TH>;
   constexpr int NMW = 3 * TH / 2;        // matrix warps
-  constexpr int NT = (NMW + 2) * 32;     // threads
-  constexpr int NC = TH + 1;
+  constexpr int NMT = NMW * 32;          // matrix threads
+  constexpr int NT = NMT + 64;           // threads
   extern __shared__ __align__(16) unsigned char smem_raw[];
   S &s = *reinterpret_cast<S *>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool is_aux = warp >= NMW;
+  const int at = tid - NMT;  // aux thread index 0..63
   const int y0 = blockIdx.y * TH;
   const int th = min(TH, a.ny - y0);
   const bool has_halo = y0 + th < a.ny;
@@ -87,11 +98,16 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
   {
     double *z = &s.even[0][0];
     for (int k = tid; k < 3 * S::EVEN_SZ + 2 * S::ODD_SZ; k += NT) z[k] = 0.0;  // even[3], odd[2] are contiguous
+    for (int k = tid; k < 36; k += NT) {
+      s.tphi[0][k] = cc.sphi[0][k]; s.tdx[0][k] = cc.sdx[0][k]; s.tdy[0][k] = cc.sdy[0][k];
+    }
+    if (tid < 4) s.tw[tid] = cc.w[tid];
+    if (tid < 12) { s.twpsi[0][tid] = cc.wpsi[0][tid]; s.tpsi[0][tid] = cc.psi[0][tid]; }
   }
   // ---- static list descriptors
   for (int tk = tid; tk < S::NDESC; tk += NT) {
     CtDesc d;
-    if (tk < 3 * (2 * TH + 1) * 3) {
+    if (tk < S::NNODE * 3) {
       const int per_line = (2 * TH + 1) * 3;
       const int ln = tk / per_line, r = tk - ln * per_line, jp = r / 3, k = r - jp * 3;
       const bool odd_j = jp & 1;
@@ -112,7 +128,7 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
       d.line = (uint8_t)ln;
       d.jp = (uint8_t)jp;
     } else {
-      const int r = tk - 3 * (2 * TH + 1) * 3, cy = r / 3, p = r - cy * 3;
+      const int r = tk - S::NNODE * 3, cy = r / 3, p = r - cy * 3;
       d.gdidx = (uint16_t)(cy * 30 + 18 + p);
       d.soff = (uint16_t)(S::ODD_P0 + cy * CT_P_BLK + p * CT_P_L);
       d.roff = (uint16_t)(S::ODD_P0 + cy * CT_P_BLK + CT_P_RES + p);
@@ -121,12 +137,26 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
     }
     s.desc[tk] = d;
   }
+  // ---- residual item of this aux lane: node (ixn, jp) of the column's 3 x (2TH+1) node grid (registers)
+  const int r_ixn = at >= 0 ? at / (2 * TH + 1) : 0, r_jp = at >= 0 ? at - r_ixn * (2 * TH + 1) : 0;
+  const bool r_valid = is_aux && at < S::NNODE && r_jp >= jlo && r_jp <= 2 * th;
+  int r_cy0 = -1, r_cy1 = -1, r_nd0 = 0, r_nd1 = 0;
+  if (r_jp & 1) {
+    r_cy0 = r_jp >> 1; r_nd0 = c_ct_node[1][r_ixn < 3 ? r_ixn : 0];
+  } else {
+    const int c0 = r_jp >> 1, c1 = (r_jp >> 1) - 1;  // node is the bottom of c0 and the top of c1
+    if (c0 < ncol_cells) { r_cy0 = c0; r_nd0 = c_ct_node[0][r_ixn < 3 ? r_ixn : 0]; }
+    if (c1 >= 0 && c1 < th) { r_cy1 = c1; r_nd1 = c_ct_node[2][r_ixn < 3 ? r_ixn : 0]; }
+  }
+  if (r_cy0 >= ncol_cells) r_cy0 = -1;
+  const int r_dst = (r_ixn == 1) ? (r_jp >> 1) * CT_ODD_STRIDE + ((r_jp & 1) ? CT_EDG_BLK + CT_CEN_RES : CT_EDG_RES)
+                                 : (r_jp >> 1) * CT_EVEN_STRIDE + ((r_jp & 1) ? CT_VTX_BLK + CT_EDG_RES : CT_VTX_RES);
 
   // ---- lane role (matrix warps): task type (bottom/mid/top third), cell slot, (major node, minor node)
   const int tt = warp % 3, slot = warp / 3;
-  const int Mi = lane / 9, mi = lane - Mi * 9;
-  const bool pair_lane = lane < 27 && !is_aux;
-  const int ixM = lane < 27 ? Mi : 0, iyM = tt;
+  const bool lane_on = lane < 27;
+  const int Mi = lane_on ? lane / 9 : 0, mi = lane_on ? lane - Mi * 9 : 0;
+  const int ixM = Mi, iyM = tt;
   const int M = c_ct_node[iyM][ixM];
   const int it = CSR ? M : mi, jt = CSR ? mi : M;
   double TA[4], TB[4], TC[4], TD[4], TM[4], TP[4], TK, TUT0, TUT1;
@@ -136,26 +166,35 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
     for (int q = 0; q < 4; ++q) { TA[q] = t.TA[q]; TB[q] = t.TB[q]; TC[q] = t.TC[q]; TD[q] = t.TD[q]; TM[q] = t.TM[q]; TP[q] = t.TP[q]; }
     TK = t.TK; TUT0 = t.TUT0; TUT1 = t.TUT1;
   }
-  const int Ld[3] = {M, 9 + M, 21 + M};
-  const int md[3] = {mi, 9 + mi, 21 + mi};
   const bool mvtx = !(ixM & 1) && !(iyM & 1), mcen = (ixM & 1) && (iyM & 1);
-  const int lo1 = mvtx ? CT_VTX_L1 : (mcen ? CT_CEN_L1 : CT_EDG_L1);
-  const int lo2 = mvtx ? CT_VTX_L2 : (mcen ? CT_CEN_L2 : CT_EDG_L2);
-  const int ex_a = mi / 3, ex_p = mi % 3;
-  const double ex_val = (lane < 27 && mi < 6) ? (CSR ? cc.UP[ex_a * 9 + M][ex_p] : -cc.UP[ex_a * 9 + M][ex_p]) : 0.0;
+  // list offsets / capacities of the major node's three lists (doubles)
+  const int lo[3] = {0, mvtx ? CT_VTX_L1 : (mcen ? CT_CEN_L1 : CT_EDG_L1), mvtx ? CT_VTX_L2 : (mcen ? CT_CEN_L2 : CT_EDG_L2)};
+  const int capU = lo[1], capT = (mvtx ? CT_VTX_RES : (mcen ? CT_CEN_RES : CT_EDG_RES)) - lo[2];
+  const int ex_a = mi < 6 ? mi / 3 : 0, ex_p = mi % 3;  // lanes mi>=6 have no extra entry (trash of list 0)
+  const double ex_val = (lane_on && mi < 6) ? (CSR ? cc.UP[ex_a * 9 + M][ex_p] : -cc.UP[ex_a * 9 + M][ex_p]) : 0.0;
   double pv[2];
   int pl[2], pd[2];
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
-    const int e = 2 * lane + k;
+    const int e = 2 * (lane_on ? lane : 0) + k;
     pl[k] = (e / 18) % 3;
     pd[k] = e % 18;
     const double up = cc.UP[pd[k]][pl[k]];
     pv[k] = CSR ? -up : up;
   }
+  // byte offsets (relative to the major node's block + list parity) of the lane's 12 entries; entries
+  // without a slot (Dirichlet minor, idle lane) point at the trash element cap-2 of their list
+  int o[12];
   int cur_cls = -1;
-  uint8_t rk[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-  uint8_t rk_ex = 0xFF, rk_p[2] = {0xFF, 0xFF};
+  // per-lane invariant part of the block address: ((iyM>>1)*stride + sub-block) in bytes
+  const int stride_b = (ixM == 1 ? CT_ODD_STRIDE : CT_EVEN_STRIDE) * 8;
+  const int blk0_b = ((iyM >> 1) * (ixM == 1 ? CT_ODD_STRIDE : CT_EVEN_STRIDE) +
+                      ((iyM & 1) ? (ixM == 1 ? CT_EDG_BLK : CT_VTX_BLK) : 0)) * 8;
+  // tasks of this warp (kernel invariant)
+  const int cyA = 2 * slot, cyB = 2 * slot + 1;
+  const bool doA = cyA < th && (2 * cyA + iyM) >= jlo;  // (<= 2*th always holds for cy < th)
+  const bool doB = cyB < th;
+  const bool doH = tt == 0 && slot == 0 && has_halo;
 
   // ---- global-load helpers (one item = one (cell, local dof) of a column)
   const int pf_cy = tid / 30, pf_l = tid - pf_cy * 30;
@@ -164,14 +203,12 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
     return a.gdofs[((int64_t)(y0 + pf_cy) * a.nx + x) * 30 + pf_l];
   };
   const int xs = x0 > 0 ? x0 - 1 : x0;
-  // prologue: dof ids of the first two columns, values of the first
   if (pf_on) {
     s.gd[xs % 3][pf_cy][pf_l] = load_gd(xs);
     if (xs + 1 < x1) s.gd[(xs + 1) % 3][pf_cy][pf_l] = load_gd(xs + 1);
   }
   __syncthreads();
   auto fetch_col = [&](int x, double &v, long long &lb, int &ll, double &vm, double &vk, int &cl) {
-    // dependent loads of column x (its dof ids are already in shared memory)
     if (pf_on) {
       const int32_t d = s.gd[x % 3][pf_cy][pf_l];
       if (d > 0) {
@@ -206,10 +243,85 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
 
   int eL = 0, eR = 1, eI = 2;  // even buffers: left line, right line, idle (being written out / zeroed)
   bool prev_out = false;       // the previous column has completed lists waiting to be written out
-  // write-out of column xw (aux warps): one TMA bulk copy per completed list
+
+  // ---- one third of a cell matrix: 9 pair values + constant P-block entries -> shared lists
+  auto matrix_task = [&](int cy, int sb, char *lineb, char *pblk, bool with_p) {
+    // class / offsets (warp uniform branch, taken only when the class changes)
+    const int cl = s.cls[sb][cy];
+    if (cl != cur_cls) {
+      cur_cls = cl;
+      const uint8_t *t = a.ctab + (int64_t)cl * 900;
+      const int Ld[3] = {M, 9 + M, 21 + M};
+      const int md[3] = {mi, 9 + mi, 21 + mi};
+#pragma unroll
+      for (int kk = 0; kk < 3; ++kk)
+#pragma unroll
+        for (int ll = 0; ll < 3; ++ll) {
+          const int r = lane_on ? t[md[ll] * 30 + Ld[kk]] : 0xFF;
+          o[kk * 3 + ll] = (lo[kk] + (r == 0xFF ? (kk == 2 ? capT : capU) - 2 : r)) * 8;
+        }
+      {
+        const int r = (lane_on && mi < 6) ? t[(18 + ex_p) * 30 + Ld[ex_a]] : 0xFF;
+        o[9] = (lo[ex_a] + (r == 0xFF ? capU - 2 : r)) * 8;
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int r = (lane_on && tt == 1) ? t[pd[k] * 30 + 18 + pl[k]] : 0xFF;
+        o[10 + k] = (pl[k] * CT_P_L + (r == 0xFF ? CT_P_L - 2 : r)) * 8;
+      }
+    }
+    double v00 = 0, v01 = 0, v10 = 0, v11 = 0, e = 0, tu0 = 0, tu1 = 0;
+    const double2 *u2 = reinterpret_cast<const double2 *>(&s.uni[cy][0][0]);
+    const double *ni = &s.nod[cy][0][it][0];
+    const double *nj = &s.nod[cy][0][jt][0];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const double2 a0 = u2[q * (CT_UNI / 2) + 0], a1 = u2[q * (CT_UNI / 2) + 1], a2 = u2[q * (CT_UNI / 2) + 2],
+                    a3 = u2[q * (CT_UNI / 2) + 3];  // (mu,G00) (G01,G10) (G11,dT0) (dT1,kap)
+      const double2 si = *reinterpret_cast<const double2 *>(ni + q * 9 * CT_NOD);
+      const double2 sj = *reinterpret_cast<const double2 *>(nj + q * 9 * CT_NOD + 2);
+      const double cj = nj[q * 9 * CT_NOD + 4];
+      const double mu = a0.x;
+      v00 = fma(mu, TA[q], v00); v11 = fma(mu, TB[q], v11); v01 = fma(mu, TC[q], v01); v10 = fma(mu, TD[q], v10);
+      if (!NEWT) {
+        v00 = fma(si.x, sj.x, v00); v01 = fma(si.x, sj.y, v01); v10 = fma(si.y, sj.x, v10); v11 = fma(si.y, sj.y, v11);
+      }
+      v00 = fma(TM[q], a0.y, v00);
+      v01 = fma(TM[q], a1.y, v01);  // (a=0,b=1): G[1][0]
+      v10 = fma(TM[q], a1.x, v10);  // (a=1,b=0): G[0][1]
+      v11 = fma(TM[q], a2.x, v11);
+      e = fma(TP[q], cj, e);
+      tu0 = fma(TM[q], a2.y, tu0);
+      tu1 = fma(TM[q], a3.x, tu1);
+    }
+    v00 += e; v11 += e;
+    const double tt_v = TK + e;
+    // block of the major node, list bases shifted by the parity of their global base (TMA alignment)
+    char *blk = lineb + blk0_b + cy * stride_b;
+    const int *lbw = reinterpret_cast<const int *>(&s.lbase[sb][cy][0]);
+    char *b0 = blk + ((lbw[2 * M] & 1) << 3);
+    char *b1 = blk + ((lbw[2 * (9 + M)] & 1) << 3);
+    char *b2 = blk + ((lbw[2 * (21 + M)] & 1) << 3);
+    if (CSR) {
+      ct_rmw(b0, o[0], v00); ct_rmw(b0, o[1], v01); ct_rmw(b0, o[2], TUT0);
+      ct_rmw(b1, o[3], v10); ct_rmw(b1, o[4], v11); ct_rmw(b1, o[5], TUT1);
+      ct_rmw(b2, o[6], tu0); ct_rmw(b2, o[7], tu1); ct_rmw(b2, o[8], tt_v);
+    } else {
+      ct_rmw(b0, o[0], v00); ct_rmw(b0, o[1], v10); ct_rmw(b0, o[2], tu0);
+      ct_rmw(b1, o[3], v01); ct_rmw(b1, o[4], v11); ct_rmw(b1, o[5], tu1);
+      ct_rmw(b2, o[6], TUT0); ct_rmw(b2, o[7], TUT1); ct_rmw(b2, o[8], tt_v);
+    }
+    ct_rmw(ex_a == 0 ? b0 : b1, o[9], ex_val);
+    if (with_p) {  // warp uniform: P major lists of this cell (mid third only)
+      char *pb = pblk + cy * (CT_P_BLK * 8);
+      ct_rmw(pb + ((lbw[2 * (18 + pl[0])] & 1) << 3), o[10], pv[0]);
+      ct_rmw(pb + ((lbw[2 * (18 + pl[1])] & 1) << 3), o[11], pv[1]);
+    }
+  };
+
+  // ---- write-out of column xw (aux warps): one TMA bulk copy per completed list
   auto write_out = [&](int xw, int bL, int bR) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    const int at = tid - NMW * 32;
     const int per_line = (2 * TH + 1) * 3;
     const int nline_tasks = ((xw == a.nx - 1) ? 3 : 2) * per_line;
     const int wb = xw & 1;
@@ -243,13 +355,14 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
             }
           }
         }
-        if (res) a.b[g - 1] = line[d.roff];
+        if (res) {
+          a.b[g - 1] = line[d.roff];
+        }
       }
     }
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   };
   auto zero_lines = [&](int be, int bo) {  // aux warps: zero an even and an odd line buffer
-    const int at = tid - NMW * 32;
     double2 *z0 = reinterpret_cast<double2 *>(s.even[be]);
     for (int k = at; k < S::EVEN_SZ / 2; k += 64) z0[k] = make_double2(0.0, 0.0);
     double2 *z1 = reinterpret_cast<double2 *>(s.odd[bo]);
@@ -265,147 +378,76 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
     const bool have_next = x + 1 < x1;
     if (!is_aux) {
       // =============================== state phase (matrix warps) ===============================
-    // S2: fields at the quadrature points.  item = (cell, q, group): group 0: u0,G00,G10 | 1: u1,G01,G11 | 2: T,dT0,dT1 | 3: p
-    for (int k = tid; k < ncol_cells * 16; k += NMW * 32) {
-      const int cy = k >> 4, q = (k >> 2) & 3, g = k & 3;
-      double *u = s.uni[cy][q];
-      if (g == 3) {
-        double v = 0;
+      // S2: fields at the quadrature points.  item = (cell, q, group): 0: u0,G00,G10 | 1: u1,G01,G11 | 2: T,dT0,dT1 | 3: p, mu, kappa
+      for (int k = tid; k < ncol_cells * 16; k += NMT) {
+        const int cy = k >> 4, q = (k >> 2) & 3, g = k & 3;
+        double *u = s.uni[cy][q];
+        if (g == 3) {
+          double v = 0;
 #pragma unroll
-        for (int m = 0; m < 3; ++m) v += cc.psi[q][m] * s.val[sb][cy][18 + m];
-        u[U_P] = v;
-        u[U_MU] = s.visc[sb][cy][q][0];
-        u[U_KAP] = s.visc[sb][cy][q][1];
-      } else {
-        const double *vv = &s.val[sb][cy][g == 0 ? 0 : (g == 1 ? 9 : 21)];
-        double f0 = 0, f1 = 0, f2 = 0;
+          for (int m = 0; m < 3; ++m) v += s.tpsi[q][m] * s.val[sb][cy][18 + m];
+          u[U_P] = v;
+          u[U_MU] = s.visc[sb][cy][q][0];
+          u[U_KAP] = s.visc[sb][cy][q][1];
+        } else {
+          const double *vv = &s.val[sb][cy][g == 0 ? 0 : (g == 1 ? 9 : 21)];
+          double f0 = 0, f1 = 0, f2 = 0;
 #pragma unroll
-        for (int i = 0; i < 9; ++i) {
-          const double t = vv[i];
-          f0 = fma(cc.sphi[q][i], t, f0); f1 = fma(cc.sdx[q][i], t, f1); f2 = fma(cc.sdy[q][i], t, f2);
+          for (int i = 0; i < 9; ++i) {
+            const double t = vv[i];
+            f0 = fma(s.tphi[q][i], t, f0); f1 = fma(s.tdx[q][i], t, f1); f2 = fma(s.tdy[q][i], t, f2);
+          }
+          if (g == 0) { u[U_U0] = f0; u[U_G00] = f1; u[U_G10] = f2; }
+          else if (g == 1) { u[U_U1] = f0; u[U_G01] = f1; u[U_G11] = f2; }
+          else { u[U_T] = f0; u[U_DT0] = f1; u[U_DT1] = f2; }
         }
-        if (g == 0) { u[U_U0] = f0; u[U_G00] = f1; u[U_G10] = f2; }
-        else if (g == 1) { u[U_U1] = f0; u[U_G01] = f1; u[U_G11] = f2; }
-        else { u[U_T] = f0; u[U_DT0] = f1; u[U_DT1] = f2; }
       }
-    }
-    asm volatile("bar.sync 2, %0;" ::"n"(NMW * 32) : "memory");  // matrix warps only
-    // S4: per-node state; the node-0 item also derives the remaining uniform values
-    for (int k = tid; k < ncol_cells * 36; k += NMW * 32) {
-      const int cy = k / 36, r = k - cy * 36, q = r / 9, i = r - q * 9;
-      double *u = s.uni[cy][q];
-      const double u0 = u[U_U0], u1 = u[U_U1], G00 = u[U_G00], G01 = u[U_G01], G10 = u[U_G10], G11 = u[U_G11];
-      const double dx = cc.sdx[q][i], dy = cc.sdy[q][i];
-      const double D01 = 0.5 * (G01 + G10);
-      const double S0 = G00 * dx + D01 * dy;
-      const double S1 = D01 * dx + G11 * dy;
-      const double sc = a.js * cc.w[q] * 2.0 * a.Pr * u[U_KAP];
-      double *o = s.nod[cy][q][i];
-      o[0] = S0; o[1] = S1; o[2] = sc * S0; o[3] = sc * S1;
-      o[4] = u0 * dx + u1 * dy;
-      if (i == 0) {
-        u[U_CONV0] = u0 * G00 + u1 * G10;
-        u[U_CONV1] = u0 * G01 + u1 * G11;
-        u[U_UDT] = u0 * u[U_DT0] + u1 * u[U_DT1];
-        u[U_DIVU] = G00 + G11;
+      __syncwarp();
+      asm volatile("bar.sync 2, %0;" ::"n"(NMT) : "memory");  // matrix warps only
+      // S4: per-node state; the node-0 item also derives the remaining uniform values
+      for (int k = tid; k < ncol_cells * 36; k += NMT) {
+        const int cy = k / 36, r = k - cy * 36, q = r / 9, i = r - q * 9;
+        double *u = s.uni[cy][q];
+        const double u0 = u[U_U0], u1 = u[U_U1], G00 = u[U_G00], G01 = u[U_G01], G10 = u[U_G10], G11 = u[U_G11];
+        const double dx = s.tdx[q][i], dy = s.tdy[q][i];
+        const double D01 = 0.5 * (G01 + G10);
+        const double S0 = G00 * dx + D01 * dy;
+        const double S1 = D01 * dx + G11 * dy;
+        const double sc = a.js * s.tw[q] * 2.0 * a.Pr * u[U_KAP];
+        double *op = s.nod[cy][q][i];
+        op[0] = S0; op[1] = S1; op[2] = sc * S0; op[3] = sc * S1;
+        op[4] = u0 * dx + u1 * dy;
+        if (i == 0) {
+          u[U_CONV0] = u0 * G00 + u1 * G10;
+          u[U_CONV1] = u0 * G01 + u1 * G11;
+          u[U_UDT] = u0 * u[U_DT0] + u1 * u[U_DT1];
+          u[U_DIVU] = G00 + G11;
+        }
       }
-    }
     } else if (prev_out) {
-      // ============ write-out of the previous column (aux warps), overlapped with the state phase ============
-      write_out(x - 1, eI, eR);   // previous left line is this column's idle buffer; its right line (last column only) never gets here
+      // ====== write-out of the previous column (aux warps), overlapped with the state phase ======
+      write_out(x - 1, eI, eR);  // previous left line = this column's idle buffer
     }
+    __syncwarp();     // (lanes of a warp have different trip counts above: reconverge before the barrier)
     __syncthreads();  // B: state of column x ready
     if (!is_aux) {
       // ---- issue the global loads of the next columns (parked in registers over the matrix phases)
-            if (have_next) {
+      if (have_next) {
         fetch_col(x + 1, nv, nlb, nll, nvm, nvk, ncl);
         if (x + 2 < x1 && pf_on) ngd = load_gd(x + 2);
       }
       if (jac) {
         // =============================== matrix phases ===============================
-        for (int ph = 0; ph < 2; ++ph) {
-          for (int rep = 0; rep < 2; ++rep) {
-            int cy;
-            if (rep == 0) cy = 2 * slot + ph;
-            else { if (!(ph == 0 && tt == 0 && slot == 0 && has_halo)) break; cy = th; }
-            if (rep == 0 && cy >= th) continue;
-            const int jp = 2 * cy + iyM;
-            if (jp < jlo || jp > 2 * th) continue;
-            const int cl = s.cls[sb][cy];
-            if (cl != cur_cls) {
-              cur_cls = cl;
-              const uint8_t *t = a.ctab + (int64_t)cl * 900;
-              if (lane < 27) {
-  #pragma unroll
-                for (int kk = 0; kk < 3; ++kk)
-  #pragma unroll
-                  for (int ll = 0; ll < 3; ++ll) rk[kk * 3 + ll] = t[md[ll] * 30 + Ld[kk]];
-                rk_ex = mi < 6 ? t[(18 + ex_p) * 30 + Ld[ex_a]] : 0xFF;
-                if (tt == 1) {
-                  rk_p[0] = t[pd[0] * 30 + 18 + pl[0]];
-                  rk_p[1] = t[pd[1] * 30 + 18 + pl[1]];
-                }
-              }
-            }
-            if (!pair_lane) continue;
-            if (pre && ixM != 2) continue;
-            double v00 = 0, v01 = 0, v10 = 0, v11 = 0, e = 0, tu0 = 0, tu1 = 0;
-  #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const double2 *u2 = reinterpret_cast<const double2 *>(s.uni[cy][q]);
-              const double2 a0 = u2[0], a1 = u2[1], a2 = u2[2], a3 = u2[3];  // (mu,G00) (G01,G10) (G11,dT0) (dT1,kap)
-              const double2 si = *reinterpret_cast<const double2 *>(&s.nod[cy][q][it][0]);
-              const double2 sj = *reinterpret_cast<const double2 *>(&s.nod[cy][q][jt][2]);
-              const double cj = s.nod[cy][q][jt][4];
-              const double mu = a0.x;
-              v00 = fma(mu, TA[q], v00); v11 = fma(mu, TB[q], v11); v01 = fma(mu, TC[q], v01); v10 = fma(mu, TD[q], v10);
-              if (!NEWT) {
-                v00 = fma(si.x, sj.x, v00); v01 = fma(si.x, sj.y, v01); v10 = fma(si.y, sj.x, v10); v11 = fma(si.y, sj.y, v11);
-              }
-              v00 = fma(TM[q], a0.y, v00);
-              v01 = fma(TM[q], a1.y, v01);  // (a=0,b=1): G[1][0]
-              v10 = fma(TM[q], a1.x, v10);  // (a=1,b=0): G[0][1]
-              v11 = fma(TM[q], a2.x, v11);
-              e = fma(TP[q], cj, e);
-              tu0 = fma(TM[q], a2.y, tu0);
-              tu1 = fma(TM[q], a3.x, tu1);
-            }
-            v00 += e; v11 += e;
-            const double tt_v = TK + e;
-            double *line = (ixM == 1) ? s.odd[ob] : s.even[ixM == 0 ? eL : eR];
-            const int row = cy + (iyM >> 1);
-            double *blk = line + ((ixM == 1) ? row * CT_ODD_STRIDE + ((iyM & 1) ? CT_EDG_BLK : 0)
-                                             : row * CT_EVEN_STRIDE + ((iyM & 1) ? CT_VTX_BLK : 0));
-            double w9[9];
-            if (CSR) {
-              w9[0] = v00; w9[1] = v01; w9[2] = TUT0; w9[3] = v10; w9[4] = v11; w9[5] = TUT1; w9[6] = tu0; w9[7] = tu1; w9[8] = tt_v;
-            } else {
-              w9[0] = v00; w9[1] = v10; w9[2] = tu0; w9[3] = v01; w9[4] = v11; w9[5] = tu1; w9[6] = TUT0; w9[7] = TUT1; w9[8] = tt_v;
-            }
-            // list k starts at slot + parity of its global base, so that shared and global addresses
-            // are 16-byte aligned together (TMA bulk copy)
-            int par[3];
-  #pragma unroll
-            for (int kk = 0; kk < 3; ++kk) par[kk] = (int)(s.lbase[sb][cy][Ld[kk]] & 1);
-  #pragma unroll
-            for (int kk = 0; kk < 3; ++kk) {
-              double *lst = blk + (kk == 0 ? 0 : (kk == 1 ? lo1 : lo2)) + par[kk];
-  #pragma unroll
-              for (int ll = 0; ll < 3; ++ll) {
-                const uint8_t r = rk[kk * 3 + ll];
-                if (r != 0xFF) lst[r] += w9[kk * 3 + ll];
-              }
-            }
-            if (rk_ex != 0xFF) (blk + (ex_a == 0 ? par[0] : lo1 + par[1]))[rk_ex] += ex_val;
-            if (tt == 1 && cy < th && !pre) {
-              double *pb = s.odd[ob] + S::ODD_P0 + cy * CT_P_BLK;
-  #pragma unroll
-              for (int k = 0; k < 2; ++k)
-                if (rk_p[k] != 0xFF) pb[pl[k] * CT_P_L + (int)(s.lbase[sb][cy][18 + pl[k]] & 1) + rk_p[k]] += pv[k];
-            }
-          }
-          if (ph == 0) asm volatile("bar.sync 1, %0;" ::"n"(NMW * 32) : "memory");  // matrix warps only
+        char *lineb = reinterpret_cast<char *>(ixM == 1 ? s.odd[ob] : s.even[ixM == 0 ? eL : eR]);
+        char *pblk = reinterpret_cast<char *>(s.odd[ob] + S::ODD_P0);
+        const bool lane_go = !(pre && ixM != 2);  // halo column: only the right line is owned
+        if (lane_go) {
+          if (doA) matrix_task(cyA, sb, lineb, pblk, tt == 1 && !pre);
+          if (doH) matrix_task(th, sb, lineb, pblk, false);
         }
+        __syncwarp();
+        asm volatile("bar.sync 1, %0;" ::"n"(NMT) : "memory");  // matrix warps only: even rows done
+        if (lane_go && doB) matrix_task(cyB, sb, lineb, pblk, tt == 1 && !pre);
       }
       // park the prefetched column in shared memory
       if (have_next) {
@@ -415,48 +457,45 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
     } else {
       // =========================== residual gather (aux warps) ===========================
       if (res) {
-        const int at = tid - NMW * 32;
-        for (int k = at; k < 3 * (2 * TH + 1) * 3; k += 64) {
-          const int ixn = k / ((2 * TH + 1) * 3), r = k - ixn * ((2 * TH + 1) * 3), jp = r / 3, comp = r - jp * 3;
-          if (jp < jlo || jp > 2 * th || (pre && ixn != 2)) continue;
-          double acc = 0;
-          for (int side = 0; side < 2; ++side) {
-            int cy, iy;
-            if (jp & 1) { if (side) break; cy = jp >> 1; iy = 1; }
-            else { cy = (jp >> 1) - side; iy = side ? 2 : 0; }
-            if (cy < 0 || cy >= ncol_cells) continue;
-            if (cy == th && iy != 0) continue;
-            const int i = c_ct_node[iy][ixn];
+        if (r_valid && !(pre && r_ixn != 2)) {
+          double r0 = 0, r1 = 0, r2 = 0;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const double *u = s.uni[cy][q];
-              const double *nd = s.nod[cy][q][i];
-              const double ph = cc.sphi[q][i], dx = cc.sdx[q][i], dy = cc.sdy[q][i];
-              double v;
-              if (comp == 0) v = 2.0 * a.Pr * u[U_MU] * nd[0] + ph * u[U_CONV0] - dx * u[U_P] - a.RaPr * u[U_T] * a.gx * ph;
-              else if (comp == 1) v = 2.0 * a.Pr * u[U_MU] * nd[1] + ph * u[U_CONV1] - dy * u[U_P] - a.RaPr * u[U_T] * a.gy * ph;
-              else v = u[U_DT0] * dx + u[U_DT1] * dy + u[U_UDT] * ph;
-              acc += cc.w[q] * v;
+          for (int side = 0; side < 2; ++side) {
+            const int cy = side ? r_cy1 : r_cy0, i = side ? r_nd1 : r_nd0;
+            if (cy >= 0) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const double *u = s.uni[cy][q];
+                const double *nd = s.nod[cy][q][i];
+                const double w = s.tw[q];
+                const double ph = w * s.tphi[q][i], dx = w * s.tdx[q][i], dy = w * s.tdy[q][i];
+                const double m2 = 2.0 * a.Pr * w * u[U_MU], bu = a.RaPr * u[U_T];
+                r0 = fma(m2, nd[0], r0); r0 = fma(ph, u[U_CONV0] - bu * a.gx, r0); r0 = fma(-dx, u[U_P], r0);
+                r1 = fma(m2, nd[1], r1); r1 = fma(ph, u[U_CONV1] - bu * a.gy, r1); r1 = fma(-dy, u[U_P], r1);
+                r2 = fma(u[U_DT0], dx, r2); r2 = fma(u[U_DT1], dy, r2); r2 = fma(u[U_UDT], ph, r2);
+              }
             }
           }
-          double *line = (ixn == 1) ? s.odd[ob] : s.even[ixn == 0 ? eL : eR];
-          const int blk = (ixn == 1) ? (jp >> 1) * CT_ODD_STRIDE + ((jp & 1) ? CT_EDG_BLK + CT_CEN_RES : CT_EDG_RES)
-                                     : (jp >> 1) * CT_EVEN_STRIDE + ((jp & 1) ? CT_VTX_BLK + CT_EDG_RES : CT_VTX_RES);
-          line[blk + comp] += acc;
+          double *dst = ((r_ixn == 1) ? s.odd[ob] : s.even[r_ixn == 0 ? eL : eR]) + r_dst;
+          dst[0] += r0; dst[1] += r1; dst[2] += r2;
         }
         if (!pre)
           for (int k = at; k < th * 3; k += 64) {
             const int cy = k / 3, p = k - cy * 3;
             double acc = 0;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) acc += cc.wpsi[q][p] * s.uni[cy][q][U_DIVU];
+            for (int q = 0; q < 4; ++q) acc += s.twpsi[q][p] * s.uni[cy][q][U_DIVU];
             s.odd[ob][S::ODD_P0 + cy * CT_P_BLK + CT_P_RES + p] = acc;
           }
       }
       // the copies issued at the top of this iteration have drained by now: recycle their buffers
+      // (wait_group is per thread: every aux thread waits for its own copies, then all 64 meet)
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+      asm volatile("bar.sync 3, 64;" ::: "memory");
       if (prev_out) zero_lines(eI, ob ^ 1);
     }
+    __syncwarp();
     __syncthreads();  // A: lists of column x complete, recycled buffers zero
     prev_out = !pre;
     if (pre) {
@@ -467,8 +506,7 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
   }
   // last column of the chunk: write it out (including the right line at the mesh boundary)
   if (is_aux && prev_out) {
-    // after the final rotation: previous left = eI, previous right = eL
-    write_out(x1 - 1, eI, eL);
+    write_out(x1 - 1, eI, eL);  // after the final rotation: previous left = eI, previous right = eL
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
-  if (is_aux) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
