@@ -17,12 +17,13 @@ LIB_PATH = os.path.join(HERE, "libgemotion_b200.so")
 
 GM_QUAD, GM_TRI = 0, 1
 GM_LAYOUT_CSC, GM_LAYOUT_CSR = 0, 1
-GM_JACOBIAN, GM_RESIDUAL, GM_CHECK_FINITE = 1, 2, 4
+GM_JACOBIAN, GM_RESIDUAL, GM_CHECK_FINITE, GM_NO_EXCHANGE = 1, 2, 4, 8
 GM_PATH_AUTO, GM_PATH_SCATTER, GM_PATH_CART = 0, 1, 2
 
 EXPORTS = ["gm_version", "gm_last_error", "gm_create", "gm_destroy", "gm_set_params", "gm_pattern",
            "gm_get_pattern", "gm_assemble", "gm_assemble_device", "gm_host_register", "gm_host_unregister",
-           "gm_set_stream", "gm_timing", "gm_info", "gm_nccl_unique_id", "gm_comm_init"]
+           "gm_set_stream", "gm_timing", "gm_info", "gm_nccl_unique_id", "gm_comm_init",
+           "gm_iface_count", "gm_iface_pack", "gm_iface_unpack_add"]
 
 
 class GmError(RuntimeError):
@@ -47,6 +48,7 @@ class gm_desc(C.Structure):
         ("device", C.c_int32), ("path", C.c_int32),
         ("rank", C.c_int32), ("nranks", C.c_int32),
         ("cell_begin", C.c_int64), ("ncells_global", C.c_int64),
+        ("ghost_lo", C.c_int32), ("ghost_hi", C.c_int32),
     ]
 
 
@@ -69,11 +71,27 @@ def build(force=False, verbose=False):
     return LIB_PATH
 
 
+def _preload_nccl():
+    """libgemotion_b200.so needs libnccl.so.2.  PyTorch bundles its own (newer) copy; whichever
+    copy is mapped first serves both, and torch fails to import against the older system one.  So
+    map torch's copy first when it exists (no torch import needed)."""
+    import glob
+    import sysconfig
+    for base in {sysconfig.get_paths()["purelib"], sysconfig.get_paths()["platlib"]}:
+        for cand in glob.glob(os.path.join(base, "nvidia", "nccl", "lib", "libnccl.so.2")):
+            try:
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+                return
+            except OSError:
+                pass
+
+
 def lib():
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise GmError(-2, "libgemotion_b200.so not built (run __graft_entry__.build()); there is no CPU path")
+        _preload_nccl()
         L = C.CDLL(LIB_PATH)
         L.gm_last_error.restype = C.c_char_p
         L.gm_destroy.restype = None
@@ -95,7 +113,8 @@ def _p(a):
 class Handle:
     """Owns one gm_handle."""
 
-    def __init__(self, sp, layout="csc", device=0, path=GM_PATH_AUTO):
+    def __init__(self, sp, layout="csc", device=0, path=GM_PATH_AUTO, rank=0, nranks=1):
+        """`sp` from fe.build_spaces (whole mesh) or fe.build_rank_spaces (one row block of `nranks`)."""
         m, r = sp.model, sp.ref
         c = np.ascontiguousarray
         d = gm_desc()
@@ -103,9 +122,16 @@ class Handle:
         d.cell_type = m.cell_type
         d.ncells, d.nverts = m.ncells, m.nverts
         keep = {}
+        rows = getattr(sp, "rows", None)
         if m.cartesian:
             d.cartesian = 1
             d.nx, d.ny = m.partition
+            if rows is not None:
+                r0, r1, glo, ghi = rows
+                d.ny = r1 - r0 + glo + ghi
+                d.ncells = d.nx * d.ny
+                d.ghost_lo, d.ghost_hi = glo, ghi
+                d.cell_begin = (r0 - glo) * d.nx
             d.origin[0], d.origin[1] = m.origin
             d.h[0], d.h[1] = m.h
         else:
@@ -128,7 +154,9 @@ class Handle:
         keep["w"], keep["phi"], keep["dphi"], keep["psi"], keep["dgphi"] = c(r.w), c(r.phi), c(r.dphi), c(r.psi), c(r.dgphi)
         d.w, d.phi, d.dphi, d.psi, d.dgphi = _p(keep["w"]), _p(keep["phi"]), _p(keep["dphi"]), _p(keep["psi"]), _p(keep["dgphi"])
         d.device, d.path = device, path
-        d.rank, d.nranks, d.cell_begin, d.ncells_global = 0, 1, 0, m.ncells
+        d.rank, d.nranks, d.ncells_global = rank, nranks, m.ncells
+        if rows is None:
+            d.cell_begin = 0
         self._h = C.c_void_p()
         self.layout = layout
         self.n = sp.n_total
@@ -177,6 +205,22 @@ class Handle:
         _check(lib().gm_assemble_device(self._h, C.c_void_p(d_x), C.c_void_p(d_nz or 0), C.c_void_p(d_b or 0),
                                         C.c_uint32(flags), C.c_int32(1 if sync else 0)))
 
+    # ---- multi-GPU row blocks
+    def comm_init(self, id128: bytes):
+        buf = C.create_string_buffer(id128, 128)
+        _check(lib().gm_comm_init(self._h, buf))
+
+    def iface_count(self, side):
+        n = C.c_int64()
+        _check(lib().gm_iface_count(self._h, C.c_int32(side), C.byref(n)))
+        return n.value
+
+    def iface_pack(self, d_nz, d_b, d_buf, flags):
+        _check(lib().gm_iface_pack(self._h, C.c_void_p(d_nz or 0), C.c_void_p(d_b or 0), C.c_void_p(d_buf), C.c_uint32(flags)))
+
+    def iface_unpack_add(self, d_nz, d_b, d_buf, flags):
+        _check(lib().gm_iface_unpack_add(self._h, C.c_void_p(d_nz or 0), C.c_void_p(d_b or 0), C.c_void_p(d_buf), C.c_uint32(flags)))
+
     def set_stream(self, stream_ptr):
         _check(lib().gm_set_stream(self._h, C.c_void_p(stream_ptr)))
 
@@ -189,6 +233,12 @@ class Handle:
         n, p, c, b = C.c_int64(), C.c_int32(), C.c_int32(), C.c_int64()
         _check(lib().gm_info(self._h, C.byref(n), C.byref(p), C.byref(c), C.byref(b)))
         return dict(n_owned=n.value, active_path=p.value, ncolors=c.value, device_bytes=b.value)
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    _check(lib().gm_nccl_unique_id(buf))
+    return buf.raw
 
 
 def host_register(a: np.ndarray):

@@ -84,6 +84,7 @@ struct gm_cart {
 
 struct CartArgs {
   int nx, ny;
+  int row_begin, row_end;  // owned cell rows of the local table (ghost rows excluded)
   const int32_t *gdofs;
   const double *dvals;
   const int64_t *ptr;
@@ -371,7 +372,7 @@ static int gm_cart_launch1(gm_handle *h, const CartArgs &a) {
     GM_CUDA(cudaFuncSetAttribute(k_cart<TH, CSR, NEWT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     attr_set = true;
   }
-  dim3 grid((a.nx + CT_XCH - 1) / CT_XCH, (a.ny + TH - 1) / TH);
+  dim3 grid((a.nx + CT_XCH - 1) / CT_XCH, (a.row_end - a.row_begin + TH - 1) / TH);
   k_cart<TH, CSR, NEWT><<<grid, (3 * TH / 2 + 2) * 32, sm, h->stream>>>(a);
   return GM_OK;
 }
@@ -388,6 +389,7 @@ static int gm_cart_run(gm_handle *h, const double *d_x, double *d_nz, double *d_
   const gm_params &p = h->prm;
   CartArgs a;
   a.nx = h->d.nx; a.ny = h->d.ny;
+  a.row_begin = h->d.ghost_lo; a.row_end = h->d.ny - h->d.ghost_hi;
   a.gdofs = h->gdofs; a.dvals = h->dvals; a.ptr = h->ptr; a.cls = c->cls; a.ctab = c->ctab; a.visc = c->visc;
   a.tab = c->d_tab; a.cc = c->d_cell; a.x = d_x; a.nz = d_nz; a.b = d_b; a.flags = flags;
   if (const char *e = getenv("GM_CART_DBG")) a.flags |= (unsigned)atoi(e) << 8;  // experiments only
@@ -402,5 +404,6 @@ static int gm_cart_run(gm_handle *h, const double *d_x, double *d_nz, double *d_
   if (rc) return rc;
   ++*launches;
   GM_CUDA(cudaGetLastError());
+  if (!(flags & GM_NO_EXCHANGE)) return gm_multi_exchange(h, d_nz, d_b, flags, launches);
   return GM_OK;
 }

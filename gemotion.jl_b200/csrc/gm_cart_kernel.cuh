@@ -86,12 +86,12 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool is_aux = warp >= NMW;
   const int at = tid - NMT;  // aux thread index 0..63
-  const int y0 = blockIdx.y * TH;
-  const int th = min(TH, a.ny - y0);
-  const bool has_halo = y0 + th < a.ny;
+  const int y0 = a.row_begin + blockIdx.y * TH;
+  const int th = min(TH, a.row_end - y0);
+  const bool has_halo = y0 + th < a.row_end;  // (a rank's top interface line has no halo: NCCL adds the neighbour's part)
   const int ncol_cells = th + (has_halo ? 1 : 0);
   const int x0 = blockIdx.x * CT_XCH, x1 = min(a.nx, x0 + CT_XCH);
-  const int jlo = y0 == 0 ? 0 : 1;
+  const int jlo = y0 == a.row_begin ? 0 : 1;  // the first strip also assembles its bottom line (partial on rank > 0)
   const bool jac = (a.flags & GM_JACOBIAN) != 0, res = (a.flags & GM_RESIDUAL) != 0;
   const CartCell &cc = *a.cc;
 

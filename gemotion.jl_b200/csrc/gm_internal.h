@@ -58,6 +58,7 @@ struct gm_handle {
   // structured path (gm_cart.cuh)
   int active_path = GM_PATH_SCATTER;
   void *cart = nullptr;
+  void *multi = nullptr;  // gm_multi (row-block interface exchange)
   // staging for the host API
   double *d_x = nullptr, *d_b = nullptr, *d_nz = nullptr;
   int64_t d_nz_cap = 0;

@@ -11,6 +11,7 @@
 #include "gm_internal.h"
 #include "gm_pattern.cuh"
 #include "gm_scatter.cuh"
+#include "gm_multi.cuh"
 #include "gm_cart.cuh"
 
 static thread_local char g_err[1024] = "";
@@ -108,10 +109,18 @@ extern "C" int gm_create(const gm_desc *d, gm_handle **out) {
     return GM_ERR_ARG;
   }
   if (d->cartesian) {
-    if (!quad || (int64_t)d->nx * d->ny != d->ncells || !(d->h[0] > 0) || !(d->h[1] > 0)) {
+    if (!quad || (int64_t)d->nx * d->ny != d->ncells || !(d->h[0] > 0) || !(d->h[1] > 0) || d->ghost_lo < 0 || d->ghost_lo > 1 ||
+        d->ghost_hi < 0 || d->ghost_hi > 1 || d->ny - d->ghost_lo - d->ghost_hi < 1) {
       gm_set_error("gm_create: inconsistent Cartesian description");
       return GM_ERR_ARG;
     }
+    if ((d->ghost_lo || d->ghost_hi) && d->path == GM_PATH_SCATTER) {
+      gm_set_error("gm_create: row blocks with ghost rows need the structured path");
+      return GM_ERR_ARG;
+    }
+  } else if (d->ghost_lo || d->ghost_hi) {
+    gm_set_error("gm_create: row-block partition is implemented for Cartesian meshes only");
+    return GM_ERR_ARG;
   } else if (!d->coords || !d->cell_vertices || !d->dgphi || d->nverts <= 0) {
     gm_set_error("gm_create: unstructured mesh needs coords, cell_vertices and dgphi");
     return GM_ERR_ARG;
@@ -224,6 +233,7 @@ extern "C" int gm_create(const gm_desc *d, gm_handle **out) {
 extern "C" void gm_destroy(gm_handle *h) {
   if (!h) return;
   cudaSetDevice(h->dev);
+  gm_multi_destroy(h);
   gm_cart_destroy(h);
   cudaFree(h->gdofs); cudaFree(h->dvals); cudaFree(h->coords); cudaFree(h->cellv);
   cudaFree(h->ptr); cudaFree(h->idx); cudaFree(h->rank); cudaFree(h->color_cells);
@@ -258,6 +268,11 @@ extern "C" int gm_pattern(gm_handle *h, int64_t *nnz) {
     if (rc) return rc;
     if (h->active_path == GM_PATH_CART) {
       rc = gm_cart_after_pattern(h);
+      if (rc) return rc;
+    }
+    if (h->d.ghost_lo || h->d.ghost_hi) {
+      if (h->active_path != GM_PATH_CART) { gm_set_error("gm_pattern: row blocks need the structured path"); return GM_ERR_ARG; }
+      rc = gm_multi_after_pattern(h);
       if (rc) return rc;
     }
   }
@@ -409,12 +424,58 @@ extern "C" int gm_host_unregister(void *ptr) {
 }
 
 extern "C" int gm_nccl_unique_id(void *id128) {
-  (void)id128;
-  gm_set_error("gm_nccl_unique_id: multi-GPU exchange not built in this version");
-  return GM_ERR_NCCL;
+  if (!id128) { gm_set_error("gm_nccl_unique_id: null argument"); return GM_ERR_ARG; }
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  GM_NCCL(ncclGetUniqueId(&id));
+  memcpy(id128, &id, 128);
+  return GM_OK;
 }
+
 extern "C" int gm_comm_init(gm_handle *h, const void *id128) {
-  (void)h; (void)id128;
-  gm_set_error("gm_comm_init: multi-GPU exchange not built in this version");
-  return GM_ERR_NCCL;
+  if (!h || !id128) { gm_set_error("gm_comm_init: null argument"); return GM_ERR_ARG; }
+  if (h->d.nranks <= 1) return GM_OK;
+  GM_CUDA(cudaSetDevice(h->dev));
+  if (!h->multi) {
+    gm_multi *m = new (std::nothrow) gm_multi();
+    if (!m) return GM_ERR_OOM;
+    h->multi = m;
+    GM_CUDA(cudaEventCreate(&m->ev0));
+    GM_CUDA(cudaEventCreate(&m->ev1));
+  }
+  gm_multi *m = (gm_multi *)h->multi;
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  GM_NCCL(ncclCommInitRank(&m->comm, h->d.nranks, id, h->d.rank));
+  return GM_OK;
+}
+
+extern "C" int gm_iface_count(gm_handle *h, int32_t side, int64_t *ndoubles) {
+  if (!h || !ndoubles) { gm_set_error("gm_iface_count: null argument"); return GM_ERR_ARG; }
+  gm_multi *m = (gm_multi *)h->multi;
+  const gm_iface *f = m ? (side == 0 ? &m->lo : &m->hi) : nullptr;
+  *ndoubles = f ? f->nlist + f->ndof : 0;
+  return GM_OK;
+}
+
+extern "C" int gm_iface_pack(gm_handle *h, const double *d_nzval, const double *d_resid, double *d_buf, uint32_t flags) {
+  if (!h || !d_buf) { gm_set_error("gm_iface_pack: null argument"); return GM_ERR_ARG; }
+  gm_multi *m = (gm_multi *)h->multi;
+  if (!m) { gm_set_error("gm_iface_pack: handle has no interface"); return GM_ERR_STATE; }
+  GM_CUDA(cudaSetDevice(h->dev));
+  int rc = gm_iface_run(h, m->lo, false, const_cast<double *>(d_nzval), const_cast<double *>(d_resid), d_buf, flags);
+  if (rc) return rc;
+  GM_CUDA(cudaStreamSynchronize(h->stream));
+  return GM_OK;
+}
+
+extern "C" int gm_iface_unpack_add(gm_handle *h, double *d_nzval, double *d_resid, const double *d_buf, uint32_t flags) {
+  if (!h || !d_buf) { gm_set_error("gm_iface_unpack_add: null argument"); return GM_ERR_ARG; }
+  gm_multi *m = (gm_multi *)h->multi;
+  if (!m) { gm_set_error("gm_iface_unpack_add: handle has no interface"); return GM_ERR_STATE; }
+  GM_CUDA(cudaSetDevice(h->dev));
+  int rc = gm_iface_run(h, m->hi, true, d_nzval, d_resid, const_cast<double *>(d_buf), flags);
+  if (rc) return rc;
+  GM_CUDA(cudaStreamSynchronize(h->stream));
+  return GM_OK;
 }

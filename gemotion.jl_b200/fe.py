@@ -230,7 +230,7 @@ class CartesianModel(DiscreteModel):
         cy = np.repeat(np.arange(ny), nx)
         v0 = cx + cy * (nx + 1)
         self.cell_vertices = np.stack([v0, v0 + 1, v0 + nx + 1, v0 + nx + 2], axis=1).astype(np.int32)
-        self.cell_edges, self.edge_vertices = _first_encounter_edges(self.cell_vertices, self.LOCAL_EDGES)
+        self.cell_edges, self.edge_vertices = self._closed_form_edges(nx, ny, self.cell_vertices)
         # entities
         vi = np.tile(i, ny + 1)
         vj = np.repeat(j, nx + 1)
@@ -245,6 +245,46 @@ class CartesianModel(DiscreteModel):
             self.tag_to_entities["tag_%d" % k] = [k]
         self.tag_to_entities["interior"] = [9]
         self.tag_to_entities["boundary"] = list(range(1, 9))
+
+    @staticmethod
+    def _closed_form_edges(nx, ny, cell_vertices):
+        """First-encounter edge ids in closed form (identical to `_first_encounter_edges`, checked in
+        tests/test_fe.py): row 0 numbers bottom, top, (left of the first cell), right per cell; every
+        later row numbers top, (left of the first cell), right per cell."""
+        cx = np.tile(np.arange(nx, dtype=np.int64), ny)
+        cy = np.repeat(np.arange(ny, dtype=np.int64), nx)
+        row0 = cy == 0
+        # ids inside row 0: cell 0 -> bottom 0, top 1, left 2, right 3 ; cell cx>0 -> base 4+3(cx-1): bottom, top, right
+        b0 = np.where(cx == 0, 0, 4 + 3 * (cx - 1))
+        bottom0 = b0
+        top0 = b0 + 1
+        right0 = np.where(cx == 0, 3, b0 + 2)
+        # rows >= 1: base(cy) = 3nx+1 + (cy-1)(2nx+1) ; cell 0 -> top, left, right ; cell cx>0 -> top, right at base+3+2(cx-1)
+        base = 3 * nx + 1 + (cy - 1) * (2 * nx + 1)
+        b1 = base + np.where(cx == 0, 0, 3 + 2 * (cx - 1))
+        top1 = b1
+        right1 = np.where(cx == 0, b1 + 2, b1 + 1)
+        top = np.where(row0, top0, top1)
+        right = np.where(row0, right0, right1)
+        nc = nx * ny
+        topg = top.reshape(ny, nx)
+        rightg = right.reshape(ny, nx)
+        bottom = np.empty((ny, nx), dtype=np.int64)
+        bottom[0] = bottom0[:nx]
+        if ny > 1:
+            bottom[1:] = topg[:-1]
+        left = np.empty((ny, nx), dtype=np.int64)
+        left[:, 0] = np.where(np.arange(ny) == 0, 2, 3 * nx + 1 + (np.arange(ny) - 1) * (2 * nx + 1) + 1)
+        if nx > 1:
+            left[:, 1:] = rightg[:, :-1]
+        cell_edges = np.stack([bottom.reshape(-1), top, left.reshape(-1), right], axis=1).astype(np.int32)
+        nedges = 3 * nx + 1 + (ny - 1) * (2 * nx + 1)
+        ev = np.zeros((nedges, 2), dtype=np.int32)
+        cv = cell_vertices
+        for k, (a, b) in enumerate(CartesianModel.LOCAL_EDGES):
+            ev[cell_edges[:, k], 0] = np.minimum(cv[:, a], cv[:, b])
+            ev[cell_edges[:, k], 1] = np.maximum(cv[:, a], cv[:, b])
+        return cell_edges, ev
 
     @staticmethod
     def _entity(left, right, bot, top):
@@ -324,7 +364,10 @@ def _face_tag_index(entity: np.ndarray, model: DiscreteModel, tags: Sequence) ->
 
 
 def build_h1_p2(model: DiscreteModel, ncomp: int, diri_tags: Sequence,
-                diri_exprs: Optional[Sequence[Union[float, Callable]]] = None) -> H1P2Space:
+                diri_exprs: Optional[Sequence[Union[float, Callable]]] = None,
+                cells: Optional[slice] = None) -> H1P2Space:
+    """`cells`: materialise the cell tables only for this contiguous cell range (multi-GPU row
+    blocks); dof ids stay GLOBAL."""
     nv, ne, nc = model.nverts, model.nedges, model.ncells
     has_cell_node = model.cell_type == QUAD
     ent = [model.vertex_entity, model.edge_entity]
@@ -342,9 +385,10 @@ def build_h1_p2(model: DiscreteModel, ncomp: int, diri_tags: Sequence,
     if has_cell_node:
         coords.append(vc[model.cell_vertices].mean(axis=1))
     coords = np.concatenate(coords)
-    cn = [model.cell_vertices.astype(np.int64), nv + model.cell_edges.astype(np.int64)]
+    sl = cells if cells is not None else slice(0, nc)
+    cn = [model.cell_vertices[sl].astype(np.int64), nv + model.cell_edges[sl].astype(np.int64)]
     if has_cell_node:
-        cn.append((nv + ne + np.arange(nc, dtype=np.int64))[:, None])
+        cn.append((nv + ne + np.arange(nc, dtype=np.int64)[sl])[:, None])
     cell_nodes = np.concatenate(cn, axis=1)
     s = signed[cell_nodes]  # [nc, nn]
     comps = []
@@ -382,6 +426,8 @@ class Spaces:
     cell_dofs_p: np.ndarray     # [nc,3] signed 1-based; last dof of the last cell is fixed (-1)
     n_free: np.ndarray          # [3] int64 (U,P,T)
     diri_p: np.ndarray          # [1] = 0.0
+    cells: Optional[slice] = None   # local cell range of a multi-GPU row block (None: all cells)
+    rows: Optional[tuple] = None    # (r0, r1, ghost_lo, ghost_hi) cell rows owned by this rank
 
     @property
     def n_total(self):
@@ -392,15 +438,40 @@ class Spaces:
         return np.array([0, self.n_free[0], self.n_free[0] + self.n_free[1]], dtype=np.int64)
 
 
-def build_spaces(model: DiscreteModel, V_diri_tags, T_diri_tags, T_diri_expressions) -> Spaces:
+def build_spaces(model: DiscreteModel, V_diri_tags, T_diri_tags, T_diri_expressions,
+                 cells: Optional[slice] = None) -> Spaces:
     ref = reference_tables(model.cell_type, 2)
-    U = build_h1_p2(model, 2, V_diri_tags, None)  # u_noslip = (0,0)  (Solver.jl:98)
-    T = build_h1_p2(model, 1, T_diri_tags if len(T_diri_tags) else [], T_diri_expressions)
+    U = build_h1_p2(model, 2, V_diri_tags, None, cells)  # u_noslip = (0,0)  (Solver.jl:98)
+    T = build_h1_p2(model, 1, T_diri_tags if len(T_diri_tags) else [], T_diri_expressions, cells)
     nc = model.ncells
     cdp = (3 * np.arange(nc, dtype=np.int64)[:, None] + np.arange(1, 4)[None, :]).astype(np.int32)
     cdp[nc - 1, 2] = -1  # constraint=:zeromean fixes the last free dof
+    if cells is not None:
+        cdp = cdp[cells]
     n_free = np.array([U.n_free, 3 * nc - 1, T.n_free], dtype=np.int64)
-    return Spaces(model, ref, U, T, np.ascontiguousarray(cdp), n_free, np.zeros(1))
+    sp = Spaces(model, ref, U, T, np.ascontiguousarray(cdp), n_free, np.zeros(1))
+    sp.cells = cells
+    return sp
+
+
+def row_block(ny: int, rank: int, nranks: int):
+    """Owner-computes row blocks: rank owns cell rows [r0, r1); its tables also carry one
+    ghost cell row on each interior side (needed for the symbolic pattern of the interface rows).
+    Returns (r0, r1, ghost_lo, ghost_hi)."""
+    r0 = (ny * rank) // nranks
+    r1 = (ny * (rank + 1)) // nranks
+    return r0, r1, (1 if rank > 0 else 0), (1 if rank < nranks - 1 else 0)
+
+
+def build_rank_spaces(model: "CartesianModel", bc_V, bc_Ttags, bc_Texpr, rank: int, nranks: int) -> Spaces:
+    """Spaces of one rank of a Cartesian row-block partition: global dof ids, local cell tables
+    (owned rows + ghost rows)."""
+    nx, ny = model.partition
+    r0, r1, glo, ghi = row_block(ny, rank, nranks)
+    sl = slice((r0 - glo) * nx, (r1 + ghi) * nx)
+    sp = build_spaces(model, bc_V, bc_Ttags, bc_Texpr, cells=sl)
+    sp.rows = (r0, r1, glo, ghi)
+    return sp
 
 
 # --------------------------------------------------------------------------------------
@@ -515,3 +586,39 @@ def square_tri_model(n=8, jitter=0.0, seed=0) -> TriangleModel:
         bedges[(vid(n, k), vid(n, k + 1))] = 8
     tags = {k: [k] for k in range(1, 10)}
     return TriangleModel(coords, np.array(tris), vent, bedges, tags, interior_entity=9)
+
+
+def _global_ids_of_rows(sp: Spaces, local_rows: slice, nodes=None) -> np.ndarray:
+    """Sorted unique 0-based global free-dof ids of the cells in the given LOCAL cell rows
+    (optionally only of the local P2 nodes `nodes`, U both comps + T)."""
+    nx = sp.model.partition[0]
+    sl = slice(local_rows.start * nx, local_rows.stop * nx)
+    off = sp.offsets
+    u, t, p = sp.U.cell_dofs[sl], sp.T.cell_dofs[sl], sp.cell_dofs_p[sl]
+    if nodes is not None:
+        nn = sp.ref.nn
+        u = u[:, list(nodes) + [nn + k for k in nodes]]
+        t = t[:, list(nodes)]
+        p = p[:, :0]
+    ids = np.concatenate([u[u > 0].astype(np.int64) - 1, p[p > 0].astype(np.int64) - 1 + off[1],
+                          t[t > 0].astype(np.int64) - 1 + off[2]])
+    return np.unique(ids)
+
+
+def interface_dofs(sp: Spaces, side: int) -> np.ndarray:
+    """Global dof ids on the rank's lower (side 0) / upper (side 1) interface line, ascending --
+    the order both neighbours pack the exchange buffer in (csrc/gm_multi.cuh)."""
+    r0, r1, glo, ghi = sp.rows
+    if side == 0:
+        return _global_ids_of_rows(sp, slice(glo, glo + 1), nodes=(0, 1, 4)) if glo else np.zeros(0, np.int64)
+    last = glo + (r1 - r0) - 1
+    return _global_ids_of_rows(sp, slice(last, last + 1), nodes=(2, 3, 5)) if ghi else np.zeros(0, np.int64)
+
+
+def owned_dofs(sp: Spaces) -> np.ndarray:
+    """Owner-computes rule: a dof belongs to the lowest row block touching it."""
+    if getattr(sp, "rows", None) is None:
+        return np.arange(sp.n_total, dtype=np.int64)
+    r0, r1, glo, ghi = sp.rows
+    mine = _global_ids_of_rows(sp, slice(glo, glo + (r1 - r0)))
+    return np.setdiff1d(mine, interface_dofs(sp, 0), assume_unique=True)

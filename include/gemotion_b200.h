@@ -59,6 +59,7 @@ enum gm_layout { GM_LAYOUT_CSC = 0, GM_LAYOUT_CSR = 1 };
 #define GM_JACOBIAN 1u     /* jacobian!(A, op, x)   */
 #define GM_RESIDUAL 2u     /* residual!(b, op, x)   */
 #define GM_CHECK_FINITE 4u /* scan outputs for NaN/Inf on the device */
+#define GM_NO_EXCHANGE 8u  /* multi-GPU: skip the NCCL interface-row sum (caller moves the packed buffers) */
 
 /* Numeric kernels */
 enum gm_path {
@@ -111,6 +112,10 @@ typedef struct gm_desc {
    * those cells but use GLOBAL dof ids.  Single GPU: rank 0 of 1, all cells. */
   int32_t rank, nranks;
   int64_t cell_begin, ncells_global;
+  /* Cartesian row blocks: the local table holds `ghost_lo` ghost cell rows below and `ghost_hi`
+   * above the owned rows (0 or 1 each; ny counts all local rows).  Ghost cells only complete the
+   * symbolic pattern of the interface rows; they are never assembled. */
+  int32_t ghost_lo, ghost_hi;
 } gm_desc;
 
 /* Timings of the last gm_assemble / gm_assemble_device call, milliseconds, CUDA events on the
@@ -178,6 +183,13 @@ int gm_info(gm_handle *h, int64_t *n_owned, int32_t *active_path, int32_t *ncolo
  * interface-row sum of gm_assemble then runs over NCCL. */
 int gm_nccl_unique_id(void *id128);
 int gm_comm_init(gm_handle *h, const void *id128);
+
+/* Interface buffers of a row block, for callers that move them themselves (tests emulate two ranks
+ * on one GPU this way; GM_NO_EXCHANGE).  side 0 = lower interface (sent to rank-1), 1 = upper
+ * (received from rank+1).  Buffers are device pointers of gm_iface_count doubles. */
+int gm_iface_count(gm_handle *h, int32_t side, int64_t *ndoubles);
+int gm_iface_pack(gm_handle *h, const double *d_nzval, const double *d_resid, double *d_buf, uint32_t flags);
+int gm_iface_unpack_add(gm_handle *h, double *d_nzval, double *d_resid, const double *d_buf, uint32_t flags);
 
 #ifdef __cplusplus
 }

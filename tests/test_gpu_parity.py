@@ -142,3 +142,63 @@ def test_structured_equals_scatter_256(gm, gpu_lib):
     assert np.array_equal(a[2], c[2]) and np.array_equal(a[3], c[3])
     assert cases.block_scaled_err(c[0], a[0], cases.nz_blocks(sp, a[2], a[3])) <= 1e-13
     assert cases.block_scaled_err(c[1], a[1], cases.res_blocks(sp)) <= 1e-13
+
+
+@pytest.mark.parametrize("nranks,nx,ny", [(2, 9, 8), (3, 70, 19), (4, 6, 4)])
+@pytest.mark.parametrize("layout", ["csc", "csr"])
+def test_row_blocks_emulated_on_one_gpu(gm, gpu_lib, nranks, nx, ny, layout):
+    """owner-computes row blocks.  All ranks live in this process on one GPU (NCCL cannot
+    put two ranks on one device), so the packed interface buffers are handed over directly
+    (GM_NO_EXCHANGE + gm_iface_pack / gm_iface_unpack_add); bench.py --gpus N runs the same
+    kernels with ncclSend/ncclRecv in between.  Every owned row must equal the oracle's."""
+    import torch
+    capi = gm.capi
+    prm = PARAMS[1]
+    model = fe.CartesianModel((0, 1.5, 0, 1), (nx, ny))
+    full = cases.spaces(model, cases.TURAN)
+    x = fe.splitmix_iterate(full.n_total, 1234)
+    orc = Oracle(full, **prm)
+    optr, oidx = orc.pattern(layout)
+    onz, ob = orc.assemble(x, layout)
+    blocks = cases.nz_blocks(full, optr, oidx)
+    rblocks = cases.res_blocks(full)
+    dx = torch.from_numpy(x).cuda()
+    flags = capi.GM_JACOBIAN | capi.GM_RESIDUAL
+    ranks = []
+    for r in range(nranks):
+        sp = fe.build_rank_spaces(model, cases.TURAN["V"], cases.TURAN["Ttags"], cases.TURAN["Texpr"], r, nranks)
+        h = capi.Handle(sp, layout=layout, path=capi.GM_PATH_CART, rank=r, nranks=nranks)
+        h.set_params(**prm)
+        nnz = h.pattern()
+        dnz = torch.full((nnz,), float("nan"), dtype=torch.float64, device="cuda")
+        db = torch.full((full.n_total,), float("nan"), dtype=torch.float64, device="cuda")
+        h.assemble_device(dx.data_ptr(), dnz.data_ptr(), db.data_ptr(), flags | capi.GM_NO_EXCHANGE, sync=True)
+        ranks.append((sp, h, dnz, db))
+    for r in range(1, nranks):  # the "NCCL" step: lower interface of r -> upper interface of r-1
+        sp, h, dnz, db = ranks[r]
+        n = h.iface_count(0)
+        assert n == ranks[r - 1][1].iface_count(1) and n > 0
+        buf = torch.empty(n, dtype=torch.float64, device="cuda")
+        h.iface_pack(dnz.data_ptr(), db.data_ptr(), buf.data_ptr(), flags)
+        _, h2, dnz2, db2 = ranks[r - 1]
+        h2.iface_unpack_add(dnz2.data_ptr(), db2.data_ptr(), buf.data_ptr(), flags)
+    seen = np.zeros(full.n_total, dtype=np.int32)
+    for sp, h, dnz, db in ranks:
+        own = fe.owned_dofs(sp)
+        seen[own] += 1
+        ptr, idx = h.get_pattern()
+        nz, b = dnz.cpu().numpy(), db.cpu().numpy()
+        # owned rows: same column indices and values as the global oracle matrix
+        lens = ptr[own + 1] - ptr[own]
+        assert np.array_equal(lens, optr[own + 1] - optr[own])
+        loc = np.concatenate([np.arange(ptr[g], ptr[g + 1]) for g in own])
+        glb = np.concatenate([np.arange(optr[g], optr[g + 1]) for g in own])
+        assert np.array_equal(idx[loc], oidx[glb])
+        full_nz = onz.copy()
+        full_nz[glb] = nz[loc]
+        assert cases.block_scaled_err(full_nz, onz, blocks) <= TOL
+        full_b = ob.copy()
+        full_b[own] = b[own]
+        assert cases.block_scaled_err(full_b, ob, rblocks) <= TOL
+        h.close()
+    assert np.all(seen == 1)
