@@ -351,6 +351,12 @@ extern "C" int gm_assemble_device(gm_handle *h, const double *d_x, double *d_nzv
     float ms = 0;
     GM_CUDA(cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]));
     h->times.kernel_ms = ms;
+    gm_multi *m = (gm_multi *)h->multi;
+    h->times.exchange_ms = 0;
+    if (m && m->comm && !(flags & GM_NO_EXCHANGE)) {
+      GM_CUDA(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
+      h->times.exchange_ms = ms;
+    }
   }
   return GM_OK;
 }
