@@ -72,7 +72,7 @@ struct CartCell {  // constants of the P blocks (cell independent on a Cartesian
 
 struct gm_cart {
   int nclass = 0;
-  uint16_t *cls = nullptr;    // [ncells]
+  int32_t *cls = nullptr;     // [ncells] rank class of each cell
   uint8_t *ctab = nullptr;    // [nclass][900]   rank[minor][major]
   double *visc = nullptr;     // [ncells][4][2]  (mu, kappa)
   CartPairTab *d_tab = nullptr;
@@ -88,7 +88,7 @@ struct CartArgs {
   const int32_t *gdofs;
   const double *dvals;
   const int64_t *ptr;
-  const uint16_t *cls;
+  const int32_t *cls;
   const uint8_t *ctab;
   const double *visc;
   const CartPairTab *tab;
@@ -124,13 +124,13 @@ __global__ void k_ct_heads(int64_t n, const uint64_t *__restrict__ hs, int32_t *
 }
 
 __global__ void k_ct_assign(int64_t n, const int32_t *__restrict__ head, const int32_t *__restrict__ cid_incl,
-                            const int32_t *__restrict__ cell_sorted, uint16_t *__restrict__ cls, int32_t *__restrict__ rep,
+                            const int32_t *__restrict__ cell_sorted, int32_t *__restrict__ cls, int32_t *__restrict__ rep,
                             int maxclass) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int id = cid_incl[i] - 1;
   if (id >= maxclass) return;
-  cls[cell_sorted[i]] = (uint16_t)id;
+  cls[cell_sorted[i]] = id;
   if (head[i]) rep[id] = cell_sorted[i];
 }
 
@@ -155,7 +155,7 @@ __device__ __forceinline__ int ct_cap(int l) {
 }
 
 __global__ void k_ct_verify(int nx, int ny, const int32_t *__restrict__ g, const int64_t *__restrict__ ptr,
-                            const uint16_t *__restrict__ rank, const uint16_t *__restrict__ cls,
+                            const uint16_t *__restrict__ rank, const int32_t *__restrict__ cls,
                             const uint8_t *__restrict__ ctab, int *__restrict__ err) {
   int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (c >= (int64_t)nx * ny) return;
@@ -269,7 +269,7 @@ static int gm_cart_after_pattern(gm_handle *h) {
   CB(cudaMemcpyAsync(&nclass, cid + nc - 1, 4, cudaMemcpyDeviceToHost, h->stream));
   CB(cudaStreamSynchronize(h->stream));
   if (nclass > CT_MAXCLASS) { why = "too many distinct cell->nnz rank tables (irregular numbering)"; herr = 1; goto decided; }
-  CB(cudaMalloc(&c->cls, 2 * nc));
+  CB(cudaMalloc(&c->cls, 4 * nc));
   CB(cudaMalloc(&c->ctab, (size_t)nclass * 900));
   k_ct_assign<<<gm_blocks(nc, 256), 256, 0, h->stream>>>(nc, head, cid, cell2, c->cls, rep, CT_MAXCLASS);
   k_ct_table<<<gm_blocks((int64_t)nclass * 900, 256), 256, 0, h->stream>>>(nclass, rep, h->rank, c->ctab, err);
@@ -290,7 +290,7 @@ decided:
     goto done;
   }
   c->nclass = nclass;
-  h->device_bytes += 2 * nc + (int64_t)nclass * 900;
+  h->device_bytes += 4 * nc + (int64_t)nclass * 900;
   CB(cudaMalloc(&c->visc, sizeof(double) * 8 * nc));
   CB(cudaMalloc(&c->d_tab, sizeof(CartPairTab) * 81));
   CB(cudaMalloc(&c->d_cell, sizeof(CartCell)));
@@ -301,7 +301,8 @@ decided:
   h->device_bytes -= (int64_t)sizeof(uint16_t) * nc * 900;
   {
     const char *e = getenv("GM_CART_TH");
-    c->th = (e && atoi(e) == 8) ? 8 : 4;  // TH=4 (2 CTAs/SM) measured faster than TH=8 (1 CTA/SM)
+    (void)e;
+    c->th = 4;  // TH=4 (2 CTAs/SM) measured faster than TH=8 (1 CTA/SM: 30.8 vs 24.2 ms at 2048^2, v4); later versions are TH=4 only
   }
 done:
   cudaFree(hash); cudaFree(hash2); cudaFree(cell); cudaFree(cell2); cudaFree(head); cudaFree(cid); cudaFree(rep);
@@ -400,7 +401,7 @@ static int gm_cart_run(gm_handle *h, const double *d_x, double *d_nz, double *d_
     ++*launches;
   }
   const bool csr = h->d.layout == GM_LAYOUT_CSR;
-  rc = c->th == 4 ? gm_cart_launch<4>(h, a, csr, newt) : gm_cart_launch<8>(h, a, csr, newt);
+  rc = gm_cart_launch<4>(h, a, csr, newt);
   if (rc) return rc;
   ++*launches;
   GM_CUDA(cudaGetLastError());

@@ -1,18 +1,19 @@
 // gm_cart_kernel.cuh -- the sweep kernel of the structured path (see gm_cart.cuh for the design).
 //
-// CTA = 3*TH/2 matrix warps + 2 aux warps.  Per column x of the strip:
-//   matrix : state phase (fields at the quadrature points, S, u.grad(phi)) for the TH(+1 halo)
-//            cells, then two colour phases (even / odd cell rows); lane = (major node, minor node)
+// CTA = 3*TH/2 matrix warps + 2 aux warps, software-pipelined over the columns x of the strip:
+//   matrix : two colour phases (even / odd cell rows) of column x; lane = (major node, minor node)
 //            pair with its reference-element tables in registers; 9 values (+ constant P-block
 //            entries) are accumulated into the shared-memory lists without branches (entries of
-//            Dirichlet minors go to a trash element at the end of each slot)
-//   aux    : write-out of the PREVIOUS column -- one TMA bulk copy (cp.async.bulk shared->global)
-//            per completed list -- overlapped with the matrix warps' state phase, then the
-//            residual gather of this column overlapped with the matrix phases, then recycling
-//            (zeroing) of the line buffers whose copies have drained
-// Three even-line and two odd-line buffers rotate.  Global loads of the next column (dof ids two
-// columns ahead, iterate / list bases / viscosity one column ahead) are issued before the matrix
-// phases and parked in registers.
+//            Dirichlet minors go to a trash element at the end of each slot); then the state of
+//            column x+1 (fields at the quadrature points, S, u.grad(phi)) into the other state
+//            buffer.  One CTA barrier per column.
+//   aux    : concurrently: write-out of column x-1 -- one TMA bulk copy (cp.async.bulk shared->global) per
+//            completed list; residual gather of column x; recycling (zeroing) of the drained
+//            line buffers.  (Giving the aux warps the next column's state as well made them the
+//            critical path: 33.5 ms vs 24.1 ms at 2048^2.)
+// Three even-line and two odd-line buffers rotate; the per-cell state is double buffered.  The
+// global loads of column x+2 (iterate, list bases, viscosity, rank class; dof ids of x+4) are
+// cp.async (LDGSTS) copies issued by the matrix threads, so they have a full column to land.
 #pragma once
 
 __device__ __constant__ int8_t c_ct_node[3][3] = {{0, 4, 1}, {6, 8, 7}, {2, 5, 3}};  // [iy][ix] -> local node
@@ -35,15 +36,15 @@ struct CtSmem {
   static constexpr int NDESC = NNODE * 3 + TH * 3;
   double even[3][EVEN_SZ];
   double odd[2][ODD_SZ];
-  double uni[NC][4][CT_UNI];
-  double nod[NC][4][9][CT_NOD];
-  double val[2][NC][30];
-  double visc[2][NC][4][2];
+  double uni[2][NC][4][CT_UNI];
+  double nod[2][NC][4][9][CT_NOD];
+  double val[4][NC][30];
+  double visc[4][NC][4][2];
   double tphi[4][9], tdx[4][9], tdy[4][9], tw[4], twpsi[4][3], tpsi[4][3];
-  long long lbase[2][NC][30];
-  int32_t llen[2][NC][30];
-  int32_t gd[3][NC][30];
-  int32_t cls[2][NC];
+  long long lbase[4][NC][30];
+  long long lnext[4][NC][30];
+  int32_t gd[8][NC][30];
+  int32_t cls[4][NC];
   CtDesc desc[NDESC];
 };
 
@@ -137,20 +138,23 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
     }
     s.desc[tk] = d;
   }
-  // ---- residual item of this aux lane: node (ixn, jp) of the column's 3 x (2TH+1) node grid (registers)
-  const int r_ixn = at >= 0 ? at / (2 * TH + 1) : 0, r_jp = at >= 0 ? at - r_ixn * (2 * TH + 1) : 0;
-  const bool r_valid = is_aux && at < S::NNODE && r_jp >= jlo && r_jp <= 2 * th;
-  int r_cy0 = -1, r_cy1 = -1, r_nd0 = 0, r_nd1 = 0;
+  // ---- residual item of this aux lane: lane pair = node (ixn, jp) of the column's 3 x (2TH+1) node grid,
+  //      lane parity = which of the node's (up to) two cells of this column it sums
+  const int r_n = at >= 0 ? (at >> 1) : 0, r_side = at & 1;
+  const int r_ixn = r_n / (2 * TH + 1) < 3 ? r_n / (2 * TH + 1) : 0, r_jp = r_n % (2 * TH + 1);
+  const bool r_valid = is_aux && r_n < S::NNODE && r_jp >= jlo && r_jp <= 2 * th;
+  int r_cy = -1, r_nd = 0;
   if (r_jp & 1) {
-    r_cy0 = r_jp >> 1; r_nd0 = c_ct_node[1][r_ixn < 3 ? r_ixn : 0];
-  } else {
-    const int c0 = r_jp >> 1, c1 = (r_jp >> 1) - 1;  // node is the bottom of c0 and the top of c1
-    if (c0 < ncol_cells) { r_cy0 = c0; r_nd0 = c_ct_node[0][r_ixn < 3 ? r_ixn : 0]; }
-    if (c1 >= 0 && c1 < th) { r_cy1 = c1; r_nd1 = c_ct_node[2][r_ixn < 3 ? r_ixn : 0]; }
+    if (r_side == 0) { r_cy = r_jp >> 1; r_nd = c_ct_node[1][r_ixn]; }
+  } else if (r_side == 0) {  // node is the bottom of cell jp/2 ...
+    if ((r_jp >> 1) < ncol_cells) { r_cy = r_jp >> 1; r_nd = c_ct_node[0][r_ixn]; }
+  } else {                   // ... and the top of cell jp/2 - 1
+    if ((r_jp >> 1) - 1 >= 0 && (r_jp >> 1) - 1 < th) { r_cy = (r_jp >> 1) - 1; r_nd = c_ct_node[2][r_ixn]; }
   }
-  if (r_cy0 >= ncol_cells) r_cy0 = -1;
+  if (r_cy >= ncol_cells) r_cy = -1;
   const int r_dst = (r_ixn == 1) ? (r_jp >> 1) * CT_ODD_STRIDE + ((r_jp & 1) ? CT_EDG_BLK + CT_CEN_RES : CT_EDG_RES)
                                  : (r_jp >> 1) * CT_EVEN_STRIDE + ((r_jp & 1) ? CT_VTX_BLK + CT_EDG_RES : CT_VTX_RES);
+  static_assert(2 * S::NNODE <= 64, "one residual lane pair per node of the column needs TH <= 4");
 
   // ---- lane role (matrix warps): task type (bottom/mid/top third), cell slot, (major node, minor node)
   const int tt = warp % 3, slot = warp / 3;
@@ -196,58 +200,120 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
   const bool doB = cyB < th;
   const bool doH = tt == 0 && slot == 0 && has_halo;
 
-  // ---- global-load helpers (one item = one (cell, local dof) of a column)
-  const int pf_cy = tid / 30, pf_l = tid - pf_cy * 30;
-  const bool pf_on = tid < ncol_cells * 30;
-  auto load_gd = [&](int x) -> int32_t {
-    return a.gdofs[((int64_t)(y0 + pf_cy) * a.nx + x) * 30 + pf_l];
-  };
+  // ---- global-load helpers: item = one (cell, local dof) of a column; PF_N items per thread
   const int xs = x0 > 0 ? x0 - 1 : x0;
-  if (pf_on) {
-    s.gd[xs % 3][pf_cy][pf_l] = load_gd(xs);
-    if (xs + 1 < x1) s.gd[(xs + 1) % 3][pf_cy][pf_l] = load_gd(xs + 1);
-  }
-  __syncthreads();
-  auto fetch_col = [&](int x, double &v, long long &lb, int &ll, double &vm, double &vk, int &cl) {
-    if (pf_on) {
-      const int32_t d = s.gd[x % 3][pf_cy][pf_l];
-      if (d > 0) {
-        v = a.x[d - 1];
-        lb = a.ptr[d - 1];
-        ll = (int)(a.ptr[d] - lb);
+  auto gd_addr = [&](int x, int item) -> const int32_t * {
+    const int cy = item / 30, l = item - cy * 30;
+    return a.gdofs + ((int64_t)(y0 + cy) * a.nx + x) * 30 + l;
+  };
+  auto cp_async8 = [&](void *sdst, const void *gsrc) {
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(sdst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
+  };
+  auto cp_async4 = [&](void *sdst, const void *gsrc) {
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(sdst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gsrc) : "memory");
+  };
+  auto cp_async16 = [&](void *sdst, const void *gsrc) {
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(sdst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+  };
+  // asynchronous copies (LDGSTS, no registers) of one item of column x: iterate value, list base, next list base
+  auto issue_item = [&](int x, int item) {
+    const int32_t d = (&s.gd[x & 7][0][0])[item];
+    const int r = x & 3;
+    double *pv = &(&s.val[r][0][0])[item];
+    long long *pb = &(&s.lbase[r][0][0])[item], *pn = &(&s.lnext[r][0][0])[item];
+    if (d > 0) {
+      cp_async8(pv, a.x + (d - 1));
+      cp_async8(pb, a.ptr + (d - 1));
+      cp_async8(pn, a.ptr + d);
+    } else {
+      cp_async8(pv, a.dvals + (-d - 1));
+      *pb = 0; *pn = 0;
+    }
+  };
+  auto issue_cell = [&](int x, int k) {  // k = cy*4 + q : viscosity pair and (q == 0) the rank class
+    const int64_t c = (int64_t)(y0 + (k >> 2)) * a.nx + x;
+    const int r = x & 3;
+    if (!NEWT) cp_async16(&s.visc[r][k >> 2][k & 3][0], a.visc + (c * 4 + (k & 3)) * 2);
+    if ((k & 3) == 0) cp_async4(&s.cls[r][k >> 2], a.cls + c);
+  };
+  // state of one column: S2 (fields at the quadrature points) and S4 (per-node state); `nthr` threads, index `t`
+  auto state_S2 = [&](int x, int t, int nthr) {
+    const int sb = x & 1, rb = x & 3;
+    for (int k = t; k < ncol_cells * 16; k += nthr) {
+      const int cy = k >> 4, q = (k >> 2) & 3, g = k & 3;
+      double *u = s.uni[sb][cy][q];
+      if (g == 3) {
+        double v = 0;
+#pragma unroll
+        for (int m = 0; m < 3; ++m) v += s.tpsi[q][m] * s.val[rb][cy][18 + m];
+        u[U_P] = v;
+        u[U_MU] = s.visc[rb][cy][q][0];
+        u[U_KAP] = s.visc[rb][cy][q][1];
       } else {
-        v = a.dvals[-d - 1]; lb = 0; ll = 0;
+        const double *vv = &s.val[rb][cy][g == 0 ? 0 : (g == 1 ? 9 : 21)];
+        double f0 = 0, f1 = 0, f2 = 0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+          const double tv = vv[i];
+          f0 = fma(s.tphi[q][i], tv, f0); f1 = fma(s.tdx[q][i], tv, f1); f2 = fma(s.tdy[q][i], tv, f2);
+        }
+        if (g == 0) { u[U_U0] = f0; u[U_G00] = f1; u[U_G10] = f2; }
+        else if (g == 1) { u[U_U1] = f0; u[U_G01] = f1; u[U_G11] = f2; }
+        else { u[U_T] = f0; u[U_DT0] = f1; u[U_DT1] = f2; }
       }
     }
-    if (tid < ncol_cells * 4) {
-      const int64_t c = (int64_t)(y0 + (tid >> 2)) * a.nx + x;
-      if (!NEWT) { vm = a.visc[(c * 4 + (tid & 3)) * 2]; vk = a.visc[(c * 4 + (tid & 3)) * 2 + 1]; }
-      if ((tid & 3) == 0) cl = a.cls[c];
+  };
+  auto state_S4 = [&](int x, int t, int nthr) {
+    const int sb = x & 1;
+    for (int k = t; k < ncol_cells * 36; k += nthr) {
+      const int cy = k / 36, r = k - cy * 36, q = r / 9, i = r - q * 9;
+      double *u = s.uni[sb][cy][q];
+      const double u0 = u[U_U0], u1 = u[U_U1], G00 = u[U_G00], G01 = u[U_G01], G10 = u[U_G10], G11 = u[U_G11];
+      const double dx = s.tdx[q][i], dy = s.tdy[q][i];
+      const double D01 = 0.5 * (G01 + G10);
+      const double S0 = G00 * dx + D01 * dy;
+      const double S1 = D01 * dx + G11 * dy;
+      const double sc = a.js * s.tw[q] * 2.0 * a.Pr * u[U_KAP];
+      double *op = s.nod[sb][cy][q][i];
+      op[0] = S0; op[1] = S1; op[2] = sc * S0; op[3] = sc * S1;
+      op[4] = u0 * dx + u1 * dy;
+      if (i == 0) {
+        u[U_CONV0] = u0 * G00 + u1 * G10;
+        u[U_CONV1] = u0 * G01 + u1 * G11;
+        u[U_UDT] = u0 * u[U_DT0] + u1 * u[U_DT1];
+        u[U_DIVU] = G00 + G11;
+      }
     }
   };
-  auto store_col = [&](int x, double v, long long lb, int ll, double vm, double vk, int cl) {
-    const int b = x & 1;
-    if (pf_on) { s.val[b][pf_cy][pf_l] = v; s.lbase[b][pf_cy][pf_l] = lb; s.llen[b][pf_cy][pf_l] = ll; }
-    if (tid < ncol_cells * 4) {
-      s.visc[b][tid >> 2][tid & 3][0] = NEWT ? 1.0 : vm;
-      s.visc[b][tid >> 2][tid & 3][1] = NEWT ? 0.0 : vk;
-      if ((tid & 3) == 0) s.cls[b][tid >> 2] = cl;
-    }
-  };
-  {
-    double v = 0, vm = 1, vk = 0; long long lb = 0; int ll = 0, cl = 0;
-    fetch_col(xs, v, lb, ll, vm, vk, cl);
-    store_col(xs, v, lb, ll, vm, vk, cl);
+  // ---- prologue (all threads): dof ids of columns xs..xs+3, data of xs, xs+1, state of xs
+  for (int k = tid; k < 4 * S::NC * 4; k += NT) { (&s.visc[0][0][0][0])[2 * k] = 1.0; (&s.visc[0][0][0][0])[2 * k + 1] = 0.0; }
+  for (int item = tid; item < ncol_cells * 30; item += NT)
+    for (int dxc = 0; dxc < 4; ++dxc)
+      if (xs + dxc < x1) (&s.gd[(xs + dxc) & 7][0][0])[item] = *gd_addr(xs + dxc, item);
+  __syncthreads();
+  for (int dxc = 0; dxc < 2; ++dxc) {
+    if (xs + dxc >= x1) break;
+    for (int item = tid; item < ncol_cells * 30; item += NT) issue_item(xs + dxc, item);
+    for (int k = tid; k < ncol_cells * 4; k += NT) issue_cell(xs + dxc, k);
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  state_S2(xs, tid, NT);
+  __syncthreads();
+  state_S4(xs, tid, NT);
   __syncthreads();
 
   int eL = 0, eR = 1, eI = 2;  // even buffers: left line, right line, idle (being written out / zeroed)
   bool prev_out = false;       // the previous column has completed lists waiting to be written out
 
   // ---- one third of a cell matrix: 9 pair values + constant P-block entries -> shared lists
-  auto matrix_task = [&](int cy, int sb, char *lineb, char *pblk, bool with_p) {
+  auto matrix_task = [&](int cy, int sb, int rb, char *lineb, char *pblk, bool with_p) {
     // class / offsets (warp uniform branch, taken only when the class changes)
-    const int cl = s.cls[sb][cy];
+    const int cl = s.cls[rb][cy];
     if (cl != cur_cls) {
       cur_cls = cl;
       const uint8_t *t = a.ctab + (int64_t)cl * 900;
@@ -271,9 +337,9 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
       }
     }
     double v00 = 0, v01 = 0, v10 = 0, v11 = 0, e = 0, tu0 = 0, tu1 = 0;
-    const double2 *u2 = reinterpret_cast<const double2 *>(&s.uni[cy][0][0]);
-    const double *ni = &s.nod[cy][0][it][0];
-    const double *nj = &s.nod[cy][0][jt][0];
+    const double2 *u2 = reinterpret_cast<const double2 *>(&s.uni[sb][cy][0][0]);
+    const double *ni = &s.nod[sb][cy][0][it][0];
+    const double *nj = &s.nod[sb][cy][0][jt][0];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const double2 a0 = u2[q * (CT_UNI / 2) + 0], a1 = u2[q * (CT_UNI / 2) + 1], a2 = u2[q * (CT_UNI / 2) + 2],
@@ -298,7 +364,7 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
     const double tt_v = TK + e;
     // block of the major node, list bases shifted by the parity of their global base (TMA alignment)
     char *blk = lineb + blk0_b + cy * stride_b;
-    const int *lbw = reinterpret_cast<const int *>(&s.lbase[sb][cy][0]);
+    const int *lbw = reinterpret_cast<const int *>(&s.lbase[rb][cy][0]);
     char *b0 = blk + ((lbw[2 * M] & 1) << 3);
     char *b1 = blk + ((lbw[2 * (9 + M)] & 1) << 3);
     char *b2 = blk + ((lbw[2 * (21 + M)] & 1) << 3);
@@ -324,8 +390,8 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     const int per_line = (2 * TH + 1) * 3;
     const int nline_tasks = ((xw == a.nx - 1) ? 3 : 2) * per_line;
-    const int wb = xw & 1;
-    const int32_t *gdw = &s.gd[xw % 3][0][0];
+    const int wb = xw & 1, wr = xw & 3;
+    const int32_t *gdw = &s.gd[xw & 7][0][0];
     for (int tk = at; tk < 3 * per_line + th * 3; tk += 64) {
       if (tk >= nline_tasks && tk < 3 * per_line) continue;
       const CtDesc d = s.desc[tk];
@@ -338,8 +404,8 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
       double *line = d.line == 1 ? s.odd[wb] : s.even[d.line == 0 ? bL : bR];
       if (g > 0) {
         if (jac) {
-          const long long base = (&s.lbase[wb][0][0])[gi];
-          const int len = (&s.llen[wb][0][0])[gi];
+          const long long base = (&s.lbase[wr][0][0])[gi];
+          const int len = (int)((&s.lnext[wr][0][0])[gi] - base);
           const int par = (int)(base & 1);
           const double *src = line + d.soff + par;  // element k of the list lives at src[k]
           double *dst = a.nz + base;
@@ -371,132 +437,86 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
 
   for (int x = xs; x < x1; ++x) {
     const bool pre = x < x0;
-    const int sb = x & 1;        // state / value buffer of this column
+    const int sb = x & 1;        // state buffer of this column
+    const int rb = x & 3;        // value / list-base ring slot of this column
     const int ob = x & 1;        // odd (mid) line buffer of this column
-    double nv = 0, nvm = 1, nvk = 0; long long nlb = 0; int nll = 0, ncl = 0;
-    int32_t ngd = 0;
-    const bool have_next = x + 1 < x1;
     if (!is_aux) {
-      // =============================== state phase (matrix warps) ===============================
-      // S2: fields at the quadrature points.  item = (cell, q, group): 0: u0,G00,G10 | 1: u1,G01,G11 | 2: T,dT0,dT1 | 3: p, mu, kappa
-      for (int k = tid; k < ncol_cells * 16; k += NMT) {
-        const int cy = k >> 4, q = (k >> 2) & 3, g = k & 3;
-        double *u = s.uni[cy][q];
-        if (g == 3) {
-          double v = 0;
-#pragma unroll
-          for (int m = 0; m < 3; ++m) v += s.tpsi[q][m] * s.val[sb][cy][18 + m];
-          u[U_P] = v;
-          u[U_MU] = s.visc[sb][cy][q][0];
-          u[U_KAP] = s.visc[sb][cy][q][1];
-        } else {
-          const double *vv = &s.val[sb][cy][g == 0 ? 0 : (g == 1 ? 9 : 21)];
-          double f0 = 0, f1 = 0, f2 = 0;
-#pragma unroll
-          for (int i = 0; i < 9; ++i) {
-            const double t = vv[i];
-            f0 = fma(s.tphi[q][i], t, f0); f1 = fma(s.tdx[q][i], t, f1); f2 = fma(s.tdy[q][i], t, f2);
-          }
-          if (g == 0) { u[U_U0] = f0; u[U_G00] = f1; u[U_G10] = f2; }
-          else if (g == 1) { u[U_U1] = f0; u[U_G01] = f1; u[U_G11] = f2; }
-          else { u[U_T] = f0; u[U_DT0] = f1; u[U_DT1] = f2; }
-        }
+      // ---- asynchronous global->shared copies of column x+2 (dof ids of x+4): one item per thread, no registers
+      if (x + 2 < x1) {
+        if (tid < ncol_cells * 30) issue_item(x + 2, tid);
+        if (tid < ncol_cells * 4) issue_cell(x + 2, tid);
       }
-      __syncwarp();
-      asm volatile("bar.sync 2, %0;" ::"n"(NMT) : "memory");  // matrix warps only
-      // S4: per-node state; the node-0 item also derives the remaining uniform values
-      for (int k = tid; k < ncol_cells * 36; k += NMT) {
-        const int cy = k / 36, r = k - cy * 36, q = r / 9, i = r - q * 9;
-        double *u = s.uni[cy][q];
-        const double u0 = u[U_U0], u1 = u[U_U1], G00 = u[U_G00], G01 = u[U_G01], G10 = u[U_G10], G11 = u[U_G11];
-        const double dx = s.tdx[q][i], dy = s.tdy[q][i];
-        const double D01 = 0.5 * (G01 + G10);
-        const double S0 = G00 * dx + D01 * dy;
-        const double S1 = D01 * dx + G11 * dy;
-        const double sc = a.js * s.tw[q] * 2.0 * a.Pr * u[U_KAP];
-        double *op = s.nod[cy][q][i];
-        op[0] = S0; op[1] = S1; op[2] = sc * S0; op[3] = sc * S1;
-        op[4] = u0 * dx + u1 * dy;
-        if (i == 0) {
-          u[U_CONV0] = u0 * G00 + u1 * G10;
-          u[U_CONV1] = u0 * G01 + u1 * G11;
-          u[U_UDT] = u0 * u[U_DT0] + u1 * u[U_DT1];
-          u[U_DIVU] = G00 + G11;
-        }
-      }
-    } else if (prev_out) {
-      // ====== write-out of the previous column (aux warps), overlapped with the state phase ======
-      write_out(x - 1, eI, eR);  // previous left line = this column's idle buffer
-    }
-    __syncwarp();     // (lanes of a warp have different trip counts above: reconverge before the barrier)
-    __syncthreads();  // B: state of column x ready
-    if (!is_aux) {
-      // ---- issue the global loads of the next columns (parked in registers over the matrix phases)
-      if (have_next) {
-        fetch_col(x + 1, nv, nlb, nll, nvm, nvk, ncl);
-        if (x + 2 < x1 && pf_on) ngd = load_gd(x + 2);
-      }
-      if (jac) {
+      if (x + 4 < x1 && tid < ncol_cells * 30) cp_async4(&(&s.gd[(x + 4) & 7][0][0])[tid], gd_addr(x + 4, tid));
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (jac && !(a.flags & 0x2000u)) {
         // =============================== matrix phases ===============================
         char *lineb = reinterpret_cast<char *>(ixM == 1 ? s.odd[ob] : s.even[ixM == 0 ? eL : eR]);
         char *pblk = reinterpret_cast<char *>(s.odd[ob] + S::ODD_P0);
         const bool lane_go = !(pre && ixM != 2);  // halo column: only the right line is owned
         if (lane_go) {
-          if (doA) matrix_task(cyA, sb, lineb, pblk, tt == 1 && !pre);
-          if (doH) matrix_task(th, sb, lineb, pblk, false);
+          if (doA) matrix_task(cyA, sb, rb, lineb, pblk, tt == 1 && !pre);
+          if (doH) matrix_task(th, sb, rb, lineb, pblk, false);
         }
+        asm volatile("cp.async.wait_group 1;" ::: "memory");  // the copies issued ONE column ago (column x+1) have landed
         __syncwarp();
-        asm volatile("bar.sync 1, %0;" ::"n"(NMT) : "memory");  // matrix warps only: even rows done
-        if (lane_go && doB) matrix_task(cyB, sb, lineb, pblk, tt == 1 && !pre);
+        asm volatile("bar.sync 1, %0;" ::"n"(NMT) : "memory");  // matrix warps only: even rows done, column x+1 data visible
+        if (lane_go && doB) matrix_task(cyB, sb, rb, lineb, pblk, tt == 1 && !pre);
+      } else {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncwarp();
+        asm volatile("bar.sync 1, %0;" ::"n"(NMT) : "memory");
       }
-      // park the prefetched column in shared memory
-      if (have_next) {
-        store_col(x + 1, nv, nlb, nll, nvm, nvk, ncl);
-        if (x + 2 < x1 && pf_on) s.gd[(x + 2) % 3][pf_cy][pf_l] = ngd;
+      // ---- state of the next column (its values were parked in shared memory one column ago)
+      if (x + 1 < x1 && !(a.flags & 0x8000u)) {
+        state_S2(x + 1, tid, NMT);
+        __syncwarp();
+        asm volatile("bar.sync 2, %0;" ::"n"(NMT) : "memory");  // matrix warps only
+        state_S4(x + 1, tid, NMT);
       }
     } else {
-      // =========================== residual gather (aux warps) ===========================
-      if (res) {
-        if (r_valid && !(pre && r_ixn != 2)) {
-          double r0 = 0, r1 = 0, r2 = 0;
+      // ---- (2) write-out of the previous column
+      if (prev_out && !(a.flags & 0x4000u)) write_out(x - 1, eI, eR);  // previous left line = this column's idle buffer
+      // ---- (4) residual gather of this column: lane pair = (node, side); partial sums combined by shuffle
+      if (res && !(a.flags & 0x400u)) {
+        double r0 = 0, r1 = 0, r2 = 0;
+        if (r_valid && !(pre && r_ixn != 2) && r_cy >= 0) {
 #pragma unroll
-          for (int side = 0; side < 2; ++side) {
-            const int cy = side ? r_cy1 : r_cy0, i = side ? r_nd1 : r_nd0;
-            if (cy >= 0) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const double *u = s.uni[cy][q];
-                const double *nd = s.nod[cy][q][i];
-                const double w = s.tw[q];
-                const double ph = w * s.tphi[q][i], dx = w * s.tdx[q][i], dy = w * s.tdy[q][i];
-                const double m2 = 2.0 * a.Pr * w * u[U_MU], bu = a.RaPr * u[U_T];
-                r0 = fma(m2, nd[0], r0); r0 = fma(ph, u[U_CONV0] - bu * a.gx, r0); r0 = fma(-dx, u[U_P], r0);
-                r1 = fma(m2, nd[1], r1); r1 = fma(ph, u[U_CONV1] - bu * a.gy, r1); r1 = fma(-dy, u[U_P], r1);
-                r2 = fma(u[U_DT0], dx, r2); r2 = fma(u[U_DT1], dy, r2); r2 = fma(u[U_UDT], ph, r2);
-              }
-            }
+          for (int q = 0; q < 4; ++q) {
+            const double *u = s.uni[sb][r_cy][q];
+            const double *nd = s.nod[sb][r_cy][q][r_nd];
+            const double w = s.tw[q];
+            const double ph = w * s.tphi[q][r_nd], dx = w * s.tdx[q][r_nd], dy = w * s.tdy[q][r_nd];
+            const double m2 = 2.0 * a.Pr * w * u[U_MU], bu = a.RaPr * u[U_T];
+            r0 = fma(m2, nd[0], r0); r0 = fma(ph, u[U_CONV0] - bu * a.gx, r0); r0 = fma(-dx, u[U_P], r0);
+            r1 = fma(m2, nd[1], r1); r1 = fma(ph, u[U_CONV1] - bu * a.gy, r1); r1 = fma(-dy, u[U_P], r1);
+            r2 = fma(u[U_DT0], dx, r2); r2 = fma(u[U_DT1], dy, r2); r2 = fma(u[U_UDT], ph, r2);
           }
+        }
+        __syncwarp();
+        r0 += __shfl_xor_sync(0xffffffffu, r0, 1);
+        r1 += __shfl_xor_sync(0xffffffffu, r1, 1);
+        r2 += __shfl_xor_sync(0xffffffffu, r2, 1);
+        if (r_valid && !(pre && r_ixn != 2) && (at & 1) == 0) {
           double *dst = ((r_ixn == 1) ? s.odd[ob] : s.even[r_ixn == 0 ? eL : eR]) + r_dst;
           dst[0] += r0; dst[1] += r1; dst[2] += r2;
         }
-        if (!pre)
-          for (int k = at; k < th * 3; k += 64) {
-            const int cy = k / 3, p = k - cy * 3;
-            double acc = 0;
+        if (!pre && at < th * 3) {
+          const int cy = at / 3, p = at - cy * 3;
+          double acc = 0;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) acc += s.twpsi[q][p] * s.uni[cy][q][U_DIVU];
-            s.odd[ob][S::ODD_P0 + cy * CT_P_BLK + CT_P_RES + p] = acc;
-          }
+          for (int q = 0; q < 4; ++q) acc += s.twpsi[q][p] * s.uni[sb][cy][q][U_DIVU];
+          s.odd[ob][S::ODD_P0 + cy * CT_P_BLK + CT_P_RES + p] = acc;
+        }
       }
-      // the copies issued at the top of this iteration have drained by now: recycle their buffers
+      // ---- (5) recycle the buffers whose copies (issued in (2)) have drained
       // (wait_group is per thread: every aux thread waits for its own copies, then all 64 meet)
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       __syncwarp();
       asm volatile("bar.sync 3, 64;" ::: "memory");
-      if (prev_out) zero_lines(eI, ob ^ 1);
+      if (prev_out && !(a.flags & 0x800u)) zero_lines(eI, ob ^ 1);
     }
     __syncwarp();
-    __syncthreads();  // A: lists of column x complete, recycled buffers zero
+    __syncthreads();  // A: lists of column x complete, state of x+1 ready, recycled buffers zero
     prev_out = !pre;
     if (pre) {
       const int t = eL; eL = eR; eR = t;  // nothing to write out: the old left line is still all zero
