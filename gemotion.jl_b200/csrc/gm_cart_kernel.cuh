@@ -26,6 +26,10 @@ struct CtDesc {  // one output list (static part)
   uint8_t jp;      // node row inside the strip (ownership test); 255 for P lists
 };
 
+#define CT_UNI_Q 18                  // doubles per quadrature point (16 used)
+#define CT_UNI_C (4 * CT_UNI_Q + 2)  // doubles per cell
+#define CT_NOD_C (4 * 9 * CT_NOD + 2)
+
 template <int TH>
 struct CtSmem {
   static constexpr int NC = TH + 1;
@@ -36,14 +40,15 @@ struct CtSmem {
   static constexpr int NDESC = NNODE * 3 + TH * 3;
   double even[3][EVEN_SZ];
   double odd[2][ODD_SZ];
-  double uni[2][NC][4][CT_UNI];
-  double nod[2][NC][4][9][CT_NOD];
+  // per-cell state, padded so that lanes working on different cells / points hit different banks
+  double uni[2][NC * CT_UNI_C];  // [cell][q][CT_UNI_Q]
+  double nod[2][NC * CT_NOD_C];  // [cell][q][node][CT_NOD]
   double val[4][NC][30];
   double visc[4][NC][4][2];
   double tphi[4][9], tdx[4][9], tdy[4][9], tw[4], twpsi[4][3], tpsi[4][3];
   long long lbase[4][NC][30];
   long long lnext[4][NC][30];
-  int32_t gd[8][NC][30];
+  int32_t gd[6][NC][30];
   int32_t cls[4][NC];
   CtDesc desc[NDESC];
 };
@@ -69,6 +74,14 @@ struct CtSmem {
 __device__ __forceinline__ void ct_bulk_store(double *gdst, const double *ssrc, int bytes) {
   const uint32_t sa = (uint32_t)__cvta_generic_to_shared(ssrc);
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(sa), "r"(bytes) : "memory");
+}
+
+// three read-modify-writes to DISTINCT elements (or trash): loads first, so the three latencies overlap
+__device__ __forceinline__ void ct_rmw3(char *base, int o0, int o1, int o2, double v0, double v1, double v2) {
+  double *p0 = reinterpret_cast<double *>(base + o0), *p1 = reinterpret_cast<double *>(base + o1),
+         *p2 = reinterpret_cast<double *>(base + o2);
+  const double a0 = *p0, a1 = *p1, a2 = *p2;
+  *p0 = a0 + v0; *p1 = a1 + v1; *p2 = a2 + v2;
 }
 
 __device__ __forceinline__ void ct_rmw(char *base, int off, double v) {
@@ -220,7 +233,7 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
   };
   // asynchronous copies (LDGSTS, no registers) of one item of column x: iterate value, list base, next list base
   auto issue_item = [&](int x, int item) {
-    const int32_t d = (&s.gd[x & 7][0][0])[item];
+    const int32_t d = (&s.gd[x % 6][0][0])[item];
     const int r = x & 3;
     double *pv = &(&s.val[r][0][0])[item];
     long long *pb = &(&s.lbase[r][0][0])[item], *pn = &(&s.lnext[r][0][0])[item];
@@ -244,7 +257,7 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
     const int sb = x & 1, rb = x & 3;
     for (int k = t; k < ncol_cells * 16; k += nthr) {
       const int cy = k >> 4, q = (k >> 2) & 3, g = k & 3;
-      double *u = s.uni[sb][cy][q];
+      double *u = &s.uni[sb][cy * CT_UNI_C + q * CT_UNI_Q];
       if (g == 3) {
         double v = 0;
 #pragma unroll
@@ -270,14 +283,14 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
     const int sb = x & 1;
     for (int k = t; k < ncol_cells * 36; k += nthr) {
       const int cy = k / 36, r = k - cy * 36, q = r / 9, i = r - q * 9;
-      double *u = s.uni[sb][cy][q];
+      double *u = &s.uni[sb][cy * CT_UNI_C + q * CT_UNI_Q];
       const double u0 = u[U_U0], u1 = u[U_U1], G00 = u[U_G00], G01 = u[U_G01], G10 = u[U_G10], G11 = u[U_G11];
       const double dx = s.tdx[q][i], dy = s.tdy[q][i];
       const double D01 = 0.5 * (G01 + G10);
       const double S0 = G00 * dx + D01 * dy;
       const double S1 = D01 * dx + G11 * dy;
       const double sc = a.js * s.tw[q] * 2.0 * a.Pr * u[U_KAP];
-      double *op = s.nod[sb][cy][q][i];
+      double *op = &s.nod[sb][cy * CT_NOD_C + (q * 9 + i) * CT_NOD];
       op[0] = S0; op[1] = S1; op[2] = sc * S0; op[3] = sc * S1;
       op[4] = u0 * dx + u1 * dy;
       if (i == 0) {
@@ -292,7 +305,7 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
   for (int k = tid; k < 4 * S::NC * 4; k += NT) { (&s.visc[0][0][0][0])[2 * k] = 1.0; (&s.visc[0][0][0][0])[2 * k + 1] = 0.0; }
   for (int item = tid; item < ncol_cells * 30; item += NT)
     for (int dxc = 0; dxc < 4; ++dxc)
-      if (xs + dxc < x1) (&s.gd[(xs + dxc) & 7][0][0])[item] = *gd_addr(xs + dxc, item);
+      if (xs + dxc < x1) (&s.gd[(xs + dxc) % 6][0][0])[item] = *gd_addr(xs + dxc, item);
   __syncthreads();
   for (int dxc = 0; dxc < 2; ++dxc) {
     if (xs + dxc >= x1) break;
@@ -324,7 +337,7 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
 #pragma unroll
         for (int ll = 0; ll < 3; ++ll) {
           const int r = lane_on ? t[md[ll] * 30 + Ld[kk]] : 0xFF;
-          o[kk * 3 + ll] = (lo[kk] + (r == 0xFF ? (kk == 2 ? capT : capU) - 2 : r)) * 8;
+          o[kk * 3 + ((ll < 2 && (mi & 1)) ? 1 - ll : ll)] = (lo[kk] + (r == 0xFF ? (kk == 2 ? capT : capU) - 2 : r)) * 8;
         }
       {
         const int r = (lane_on && mi < 6) ? t[(18 + ex_p) * 30 + Ld[ex_a]] : 0xFF;
@@ -337,13 +350,13 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
       }
     }
     double v00 = 0, v01 = 0, v10 = 0, v11 = 0, e = 0, tu0 = 0, tu1 = 0;
-    const double2 *u2 = reinterpret_cast<const double2 *>(&s.uni[sb][cy][0][0]);
-    const double *ni = &s.nod[sb][cy][0][it][0];
-    const double *nj = &s.nod[sb][cy][0][jt][0];
+    const double2 *u2 = reinterpret_cast<const double2 *>(&s.uni[sb][cy * CT_UNI_C]);
+    const double *ni = &s.nod[sb][cy * CT_NOD_C + it * CT_NOD];
+    const double *nj = &s.nod[sb][cy * CT_NOD_C + jt * CT_NOD];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const double2 a0 = u2[q * (CT_UNI / 2) + 0], a1 = u2[q * (CT_UNI / 2) + 1], a2 = u2[q * (CT_UNI / 2) + 2],
-                    a3 = u2[q * (CT_UNI / 2) + 3];  // (mu,G00) (G01,G10) (G11,dT0) (dT1,kap)
+      const double2 a0 = u2[q * (CT_UNI_Q / 2) + 0], a1 = u2[q * (CT_UNI_Q / 2) + 1], a2 = u2[q * (CT_UNI_Q / 2) + 2],
+                    a3 = u2[q * (CT_UNI_Q / 2) + 3];  // (mu,G00) (G01,G10) (G11,dT0) (dT1,kap)
       const double2 si = *reinterpret_cast<const double2 *>(ni + q * 9 * CT_NOD);
       const double2 sj = *reinterpret_cast<const double2 *>(nj + q * 9 * CT_NOD + 2);
       const double cj = nj[q * 9 * CT_NOD + 4];
@@ -368,15 +381,15 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
     char *b0 = blk + ((lbw[2 * M] & 1) << 3);
     char *b1 = blk + ((lbw[2 * (9 + M)] & 1) << 3);
     char *b2 = blk + ((lbw[2 * (21 + M)] & 1) << 3);
-    if (CSR) {
-      ct_rmw(b0, o[0], v00); ct_rmw(b0, o[1], v01); ct_rmw(b0, o[2], TUT0);
-      ct_rmw(b1, o[3], v10); ct_rmw(b1, o[4], v11); ct_rmw(b1, o[5], TUT1);
-      ct_rmw(b2, o[6], tu0); ct_rmw(b2, o[7], tu1); ct_rmw(b2, o[8], tt_v);
-    } else {
-      ct_rmw(b0, o[0], v00); ct_rmw(b0, o[1], v10); ct_rmw(b0, o[2], tu0);
-      ct_rmw(b1, o[3], v01); ct_rmw(b1, o[4], v11); ct_rmw(b1, o[5], tu1);
-      ct_rmw(b2, o[6], TUT0); ct_rmw(b2, o[7], TUT1); ct_rmw(b2, o[8], tt_v);
-    }
+    // entries (list k, minor ux) and (list k, minor uy) sit at even / odd positions of the list: lanes
+    // with an odd minor node handle them in swapped order so one warp access covers both bank parities
+    const bool sw = mi & 1;
+    double e00, e01, e02, e10, e11, e12, e20, e21, e22;  // [list k][minor dof l]
+    if (CSR) { e00 = v00; e01 = v01; e02 = TUT0; e10 = v10; e11 = v11; e12 = TUT1; e20 = tu0; e21 = tu1; e22 = tt_v; }
+    else     { e00 = v00; e01 = v10; e02 = tu0;  e10 = v01; e11 = v11; e12 = tu1;  e20 = TUT0; e21 = TUT1; e22 = tt_v; }
+    ct_rmw3(b0, o[0], o[1], o[2], sw ? e01 : e00, sw ? e00 : e01, e02);
+    ct_rmw3(b1, o[3], o[4], o[5], sw ? e11 : e10, sw ? e10 : e11, e12);
+    ct_rmw3(b2, o[6], o[7], o[8], sw ? e21 : e20, sw ? e20 : e21, e22);
     ct_rmw(ex_a == 0 ? b0 : b1, o[9], ex_val);
     if (with_p) {  // warp uniform: P major lists of this cell (mid third only)
       char *pb = pblk + cy * (CT_P_BLK * 8);
@@ -391,7 +404,7 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
     const int per_line = (2 * TH + 1) * 3;
     const int nline_tasks = ((xw == a.nx - 1) ? 3 : 2) * per_line;
     const int wb = xw & 1, wr = xw & 3;
-    const int32_t *gdw = &s.gd[xw & 7][0][0];
+    const int32_t *gdw = &s.gd[xw % 6][0][0];
     for (int tk = at; tk < 3 * per_line + th * 3; tk += 64) {
       if (tk >= nline_tasks && tk < 3 * per_line) continue;
       const CtDesc d = s.desc[tk];
@@ -446,7 +459,7 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
         if (tid < ncol_cells * 30) issue_item(x + 2, tid);
         if (tid < ncol_cells * 4) issue_cell(x + 2, tid);
       }
-      if (x + 4 < x1 && tid < ncol_cells * 30) cp_async4(&(&s.gd[(x + 4) & 7][0][0])[tid], gd_addr(x + 4, tid));
+      if (x + 4 < x1 && tid < ncol_cells * 30) cp_async4(&(&s.gd[(x + 4) % 6][0][0])[tid], gd_addr(x + 4, tid));
       asm volatile("cp.async.commit_group;" ::: "memory");
       if (jac && !(a.flags & 0x2000u)) {
         // =============================== matrix phases ===============================
@@ -482,8 +495,8 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
         if (r_valid && !(pre && r_ixn != 2) && r_cy >= 0) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const double *u = s.uni[sb][r_cy][q];
-            const double *nd = s.nod[sb][r_cy][q][r_nd];
+            const double *u = &s.uni[sb][r_cy * CT_UNI_C + q * CT_UNI_Q];
+            const double *nd = &s.nod[sb][r_cy * CT_NOD_C + (q * 9 + r_nd) * CT_NOD];
             const double w = s.tw[q];
             const double ph = w * s.tphi[q][r_nd], dx = w * s.tdx[q][r_nd], dy = w * s.tdy[q][r_nd];
             const double m2 = 2.0 * a.Pr * w * u[U_MU], bu = a.RaPr * u[U_T];
@@ -504,7 +517,7 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
           const int cy = at / 3, p = at - cy * 3;
           double acc = 0;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) acc += s.twpsi[q][p] * s.uni[sb][cy][q][U_DIVU];
+          for (int q = 0; q < 4; ++q) acc += s.twpsi[q][p] * s.uni[sb][cy * CT_UNI_C + q * CT_UNI_Q + U_DIVU];
           s.odd[ob][S::ODD_P0 + cy * CT_P_BLK + CT_P_RES + p] = acc;
         }
       }
