@@ -202,3 +202,21 @@ def test_row_blocks_emulated_on_one_gpu(gm, gpu_lib, nranks, nx, ny, layout):
         assert cases.block_scaled_err(full_b, ob, rblocks) <= TOL
         h.close()
     assert np.all(seen == 1)
+
+
+@pytest.mark.parametrize("n,bc,N", [(0.6, "WAVE", 16), (1.0, "SIMPLE", 20)])
+def test_newton_through_the_plugin_matches_oracle_newton(gm, gpu_lib, n, bc, N):
+    """north_star: 'Newton converges in the same iteration count with fields within 1e-10'.
+    Same driver (NLsolve newton_ + BackTracking restated in solver.py), operator = B200 plug-in vs oracle."""
+    from orc_operator import OracleOperator
+    sp = cases.cart(N, bc=getattr(cases, bc))
+    prm = dict(Pr=100.0, Ra=1e4, n=n) if bc == "WAVE" else dict(Pr=0.7, Ra=1e3, n=n)
+    ref = gm.solver.newton(OracleOperator(sp, **prm), np.zeros(sp.n_total), ftol=1e-8, xtol=1e-50, iterations=60)
+    op = gm.operator.B200FEOperator(sp, **prm)
+    try:
+        got = gm.solver.newton(op, np.zeros(sp.n_total), ftol=1e-8, xtol=1e-50, iterations=60)
+    finally:
+        op.close()
+    assert ref.f_converged and got.f_converged
+    assert got.iterations == ref.iterations and got.f_calls == ref.f_calls
+    assert np.max(np.abs(got.x - ref.x)) <= 1e-10 * max(1.0, np.max(np.abs(ref.x)))
