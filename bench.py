@@ -257,9 +257,24 @@ def main():
     # ---- e2e through the C ABI with host buffers ----
     e2e = None
     e2e_note = None
-    if not args.no_e2e and 8 * nnz > 40e9 and not args.force_e2e:
-        e2e_note = "skipped: %.0f GB of pinned host memory per rank needed for nzval (use --force-e2e)" % (8 * nnz / 1e9)
-        args.no_e2e = True
+    if not args.no_e2e and not args.force_e2e:
+        # pinned host buffers of this rank's outputs; never risk the box: need 2.5x headroom in this rank's RAM share
+        need = 8 * nnz + 16 * sp.n_total
+        try:
+            import psutil
+            avail = psutil.virtual_memory().available / max(world, 1)
+        except Exception:
+            avail = 64e9
+        if need * 2.5 > avail or need > 40e9:
+            e2e_note = "skipped: %.0f GB of pinned host memory per rank needed, %.0f GB available per rank (use --force-e2e)" % (need / 1e9, avail / 1e9)
+            args.no_e2e = True
+    if world > 1:  # every rank must take the same branch (gm_assemble is collective)
+        flag = torch.tensor([1 if args.no_e2e else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if int(flag.item()) and not args.no_e2e:
+            args.no_e2e = True
+            e2e_note = "skipped: another rank lacks host memory for pinned buffers"
+
     if not args.no_e2e:
         xh = torch.from_numpy(x_host).pin_memory()
         nzh = torch.empty(nnz, dtype=torch.float64).pin_memory()
