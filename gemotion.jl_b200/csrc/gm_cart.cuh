@@ -4,12 +4,13 @@
 // residual_and_jacobian! of the operator built at /root/reference/src/Solver.jl:157, integrands
 // Solver.jl:111-152, arithmetic SURVEY.md A.4) but never read-modify-writes nzval in HBM:
 //
-//  * A CTA owns a strip of TH=8 cell rows and sweeps it column by column in x.  The value lists
+//  * A CTA owns a strip of TH=4 cell rows and sweeps it column by column in x.  The value lists
 //    (CSC columns / CSR rows) of the P2 nodes of the current column are accumulated in SHARED
 //    memory; a list is complete when the sweep has passed its node, and is then streamed to HBM
-//    exactly once, contiguously.  Cells of the strip's upper neighbour row (and of the column left
-//    of an x-chunk) are evaluated as halo, only for the lists this CTA owns, so no entry of any
-//    cell matrix is ever computed twice and no inter-CTA communication or atomics are needed.
+//    exactly once, contiguously, by a TMA bulk copy.  Cells of the strip's upper neighbour row (and
+//    of the column left of an x-chunk) are evaluated as halo, only for the lists this CTA owns, so
+//    no entry of any cell matrix is ever computed twice and no inter-CTA communication or atomics
+//    are needed.
 //  * Inside a column, a warp evaluates one third of a cell matrix: lane = (major node, minor
 //    node) pair.  The pair's reference-element products (phi_i phi_j, d phi_i d phi_j, ... times
 //    w|J|) are loop-invariant on a Cartesian mesh and live in REGISTERS; the per-cell state
@@ -18,7 +19,8 @@
 //    TDFMA/s, with register operands at 15.5 - profiles/r01_ubench_dfma_operand_source.txt.)
 //  * The cell->nnz map is table driven (rank classes): cells whose 30x30 rank table is identical
 //    share one 900-byte class table, so whatever numbering Gridap produced is honoured while the
-//    map costs 2 bytes per cell instead of 837 x 8.
+//    map costs 4 bytes per cell instead of 837 x 8.
+//  The kernel itself (pipeline, warp roles, buffers) is documented in gm_cart_kernel.cuh.
 //
 // Summation order differs from Gridap's (cells of a node are added left column first, even rows
 // before odd rows); values agree with the oracle to ~1e-15 relative (tests/test_gpu_parity.py).
@@ -300,8 +302,6 @@ decided:
   h->rank = nullptr;
   h->device_bytes -= (int64_t)sizeof(uint16_t) * nc * 900;
   {
-    const char *e = getenv("GM_CART_TH");
-    (void)e;
     c->th = 4;  // TH=4 (2 CTAs/SM) measured faster than TH=8 (1 CTA/SM: 30.8 vs 24.2 ms at 2048^2, v4); later versions are TH=4 only
   }
 done:
@@ -393,7 +393,6 @@ static int gm_cart_run(gm_handle *h, const double *d_x, double *d_nz, double *d_
   a.row_begin = h->d.ghost_lo; a.row_end = h->d.ny - h->d.ghost_hi;
   a.gdofs = h->gdofs; a.dvals = h->dvals; a.ptr = h->ptr; a.cls = c->cls; a.ctab = c->ctab; a.visc = c->visc;
   a.tab = c->d_tab; a.cc = c->d_cell; a.x = d_x; a.nz = d_nz; a.b = d_b; a.flags = flags;
-  if (const char *e = getenv("GM_CART_DBG")) a.flags |= (unsigned)atoi(e) << 8;  // experiments only
   a.Pr = p.Pr; a.RaPr = p.Ra * p.Pr; a.gx = p.gx; a.gy = p.gy; a.reg = p.reg; a.n = p.n; a.js = p.jac_scaling;
   const bool newt = p.n == 1.0;
   if (!newt) {

@@ -425,14 +425,7 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
           int k0 = 0, n = len;
           if (par) { dst[0] = src[0]; k0 = 1; n -= 1; }
           if (n & 1) { dst[k0 + n - 1] = src[k0 + n - 1]; n -= 1; }
-          if (n > 0) {
-            if (a.flags & 0x100u) {
-            } else if (a.flags & 0x200u) {
-              for (int k2 = 0; k2 < n; k2 += 2) *reinterpret_cast<double2 *>(dst + k0 + k2) = *reinterpret_cast<const double2 *>(src + k0 + k2);
-            } else {
-              ct_bulk_store(dst + k0, src + k0, n * 8);
-            }
-          }
+          if (n > 0) ct_bulk_store(dst + k0, src + k0, n * 8);
         }
         if (res) {
           a.b[g - 1] = line[d.roff];
@@ -461,7 +454,7 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
       }
       if (x + 4 < x1 && tid < ncol_cells * 30) cp_async4(&(&s.gd[(x + 4) % 6][0][0])[tid], gd_addr(x + 4, tid));
       asm volatile("cp.async.commit_group;" ::: "memory");
-      if (jac && !(a.flags & 0x2000u)) {
+      if (jac) {
         // =============================== matrix phases ===============================
         char *lineb = reinterpret_cast<char *>(ixM == 1 ? s.odd[ob] : s.even[ixM == 0 ? eL : eR]);
         char *pblk = reinterpret_cast<char *>(s.odd[ob] + S::ODD_P0);
@@ -480,7 +473,7 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
         asm volatile("bar.sync 1, %0;" ::"n"(NMT) : "memory");
       }
       // ---- state of the next column (its values were parked in shared memory one column ago)
-      if (x + 1 < x1 && !(a.flags & 0x8000u)) {
+      if (x + 1 < x1) {
         state_S2(x + 1, tid, NMT);
         __syncwarp();
         asm volatile("bar.sync 2, %0;" ::"n"(NMT) : "memory");  // matrix warps only
@@ -488,9 +481,9 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
       }
     } else {
       // ---- (2) write-out of the previous column
-      if (prev_out && !(a.flags & 0x4000u)) write_out(x - 1, eI, eR);  // previous left line = this column's idle buffer
+      if (prev_out) write_out(x - 1, eI, eR);  // previous left line = this column's idle buffer
       // ---- (4) residual gather of this column: lane pair = (node, side); partial sums combined by shuffle
-      if (res && !(a.flags & 0x400u)) {
+      if (res) {
         double r0 = 0, r1 = 0, r2 = 0;
         if (r_valid && !(pre && r_ixn != 2) && r_cy >= 0) {
 #pragma unroll
@@ -526,7 +519,7 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       __syncwarp();
       asm volatile("bar.sync 3, 64;" ::: "memory");
-      if (prev_out && !(a.flags & 0x800u)) zero_lines(eI, ob ^ 1);
+      if (prev_out) zero_lines(eI, ob ^ 1);
     }
     __syncwarp();
     __syncthreads();  // A: lists of column x complete, state of x+1 ready, recycled buffers zero

@@ -220,3 +220,13 @@ def test_newton_through_the_plugin_matches_oracle_newton(gm, gpu_lib, n, bc, N):
     assert ref.f_converged and got.f_converged
     assert got.iterations == ref.iterations and got.f_calls == ref.f_calls
     assert np.max(np.abs(got.x - ref.x)) <= 1e-10 * max(1.0, np.max(np.abs(ref.x)))
+
+
+def test_config3_annulus_kuehn_size(gm, gpu_lib):
+    """BASELINE config 3 (validation-kuehn): concentric annulus R1=5/8, R2=13/8, Pr=0.706, Ra=4.7e4, n=1, tags
+    inner/outer/all; ~4.6 k irregular triangles (the .msh files are LFS pointers, so the mesh is generated)."""
+    sp = cases.spaces(fe.annulus_model(nr=18, nt=128, jitter=0.35, seed=7), cases.KUEHN)
+    assert sp.model.ncells == 2 * 18 * 128
+    x = fe.splitmix_iterate(sp.n_total, 1234)
+    info = _check(gm, sp, dict(Pr=0.706, Ra=4.7e4, n=1.0), "csc", gm.capi.GM_PATH_AUTO, x)
+    assert info["active_path"] == gm.capi.GM_PATH_SCATTER and info["ncolors"] >= 6
