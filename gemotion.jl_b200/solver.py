@@ -179,3 +179,50 @@ def nu_bot_avg(sp, x, n_plot=100):
         _, dphi = fe.shape_at(fe.QUAD, xi, 0.0)
         out.append(-(dphi[:, 1] @ Tc[cx]) / hy)
     return float(np.sum(out) / len(out))
+
+
+# --------------------------------------------------------------------------------------
+# entropy fields of /root/reference/src/Solver.jl:281-289, sampled like examples/study1/study1.jl:251-271
+# (used only to pin the oracle's VELOCITY field against conv_study_square.csv: Sth_max, Sfl_max)
+# --------------------------------------------------------------------------------------
+def _cell_values(space, x, off):
+    d = space.cell_dofs
+    return np.where(d > 0, x[off + np.maximum(d, 1) - 1], space.diri_values[np.maximum(-d, 1) - 1])
+
+
+def entropy_fields_max(sp, x, n_plot=100):
+    """(Sth_max, Sfl_max): nodal interpolation of |grad T|^2 and 1e-4*(2(dx ux^2 + dy uy^2) + (dy ux + dx uy)^2)
+    into a Q2 H1 space (cell by cell, the last cell writes shared nodes), evaluated on the n_plot x n_plot
+    grid of LinRange(0,1) points and maximised."""
+    from . import fe
+    m = sp.model
+    nx, ny = m.partition
+    hx, hy = m.h
+    nn = sp.ref.nn
+    Uc = _cell_values(sp.U, x, sp.offsets[0])          # [nc, 18]
+    Tc = _cell_values(sp.T, x, sp.offsets[2])          # [nc, 9]
+    nodes = sp.ref.nodes
+    dph = np.array([fe.shape_at(fe.QUAD, a, b)[1] for a, b in nodes])   # [node p][shape i][2] reference gradients
+    dph = dph / np.array([hx, hy])
+    gT = np.einsum("pik,ci->cpk", dph, Tc)                               # grad T at the 9 nodes of each cell
+    sth = (gT ** 2).sum(axis=2)
+    G = np.stack([np.einsum("pik,ci->cpk", dph, Uc[:, :nn]), np.einsum("pik,ci->cpk", dph, Uc[:, nn:])], axis=3)  # [c,p,k,a] = d_k u_a
+    sfl = 1e-4 * (2.0 * (G[:, :, 0, 0] ** 2 + G[:, :, 1, 1] ** 2) + (G[:, :, 0, 1] + G[:, :, 1, 0]) ** 2)
+    nnode = sp.T.node_coords.shape[0]
+    out = []
+    for cellvals in (sth, sfl):
+        nodal = np.zeros(nnode)
+        nodal[sp.T.cell_nodes.reshape(-1)] = cellvals.reshape(-1)       # later cells overwrite earlier ones
+        best = -np.inf
+        xs = np.linspace(0.0, 1.0, n_plot)
+        for Y in xs:
+            cy = min(int(math.floor((Y - m.origin[1]) / hy)), ny - 1)
+            eta = (Y - (m.origin[1] + cy * hy)) / hy
+            for X in xs:
+                cx = min(int(math.floor((X - m.origin[0]) / hx)), nx - 1)
+                xi = (X - (m.origin[0] + cx * hx)) / hx
+                phi, _ = fe.shape_at(fe.QUAD, xi, eta)
+                v = float(phi @ nodal[sp.T.cell_nodes[cx + cy * nx]])
+                best = max(best, v)
+        out.append(best)
+    return tuple(out)

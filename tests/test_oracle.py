@@ -23,6 +23,11 @@ def test_golden_nu_62(gm):
     assert np.max(np.abs(b)) <= 1e-8  # ftol of study1.jl:82
     nu = gm.solver.nu_bot_avg(sp, x)
     assert abs(nu - NU_GOLD[62]) / NU_GOLD[62] < 1e-13, nu
+    # the same CSV row also pins the VELOCITY field: Sth_max (|grad T|^2) and Sfl_max (viscous dissipation),
+    # src/Solver.jl:281-289 sampled as in examples/study1/study1.jl:251-271
+    sth, sfl = gm.solver.entropy_fields_max(sp, x)
+    assert abs(sth - 104.37198885839547) / 104.37198885839547 < 1e-12, sth
+    assert abs(sfl - 2406.6836086605012) / 2406.6836086605012 < 5e-12, sfl
 
 
 @pytest.mark.skipif(os.environ.get("GM_SLOW") != "1", reason="2 min Newton run; GM_SLOW=1")
