@@ -28,7 +28,6 @@ struct CtDesc {  // one output list (static part)
 
 #define CT_UNI_Q 18                  // doubles per quadrature point (16 used)
 #define CT_UNI_C (4 * CT_UNI_Q + 2)  // doubles per cell
-#define CT_NOD_C (4 * 9 * CT_NOD + 2)
 
 template <int TH>
 struct CtSmem {
@@ -42,10 +41,10 @@ struct CtSmem {
   double odd[2][ODD_SZ];
   // per-cell state, padded so that lanes working on different cells / points hit different banks
   double uni[2][NC * CT_UNI_C];  // [cell][q][CT_UNI_Q]
-  double nod[2][NC * CT_NOD_C];  // [cell][q][node][CT_NOD]
   double val[4][NC][30];
   double visc[4][NC][4][2];
   double tphi[4][9], tdx[4][9], tdy[4][9], tw[4], twpsi[4][3], tpsi[4][3];
+  double tdxy[4][9][2];  // (d_x phi_i, d_y phi_i) pairs for 128-bit loads
   long long lbase[4][NC][30];
   long long lnext[4][NC][30];
   int32_t gd[6][NC][30];
@@ -61,15 +60,11 @@ struct CtSmem {
 #define U_G11 4
 #define U_DT0 5
 #define U_DT1 6
-#define U_KAP 7
-#define U_CONV0 8
-#define U_CONV1 9
+#define U_SC 7   // jac_scaling * w_q|J| * 2 Pr * kappa_q
+#define U_U0 8
+#define U_U1 9
 #define U_P 10
 #define U_T 11
-#define U_UDT 12
-#define U_DIVU 13
-#define U_U0 14
-#define U_U1 15
 
 __device__ __forceinline__ void ct_bulk_store(double *gdst, const double *ssrc, int bytes) {
   const uint32_t sa = (uint32_t)__cvta_generic_to_shared(ssrc);
@@ -114,6 +109,7 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
     for (int k = tid; k < 3 * S::EVEN_SZ + 2 * S::ODD_SZ; k += NT) z[k] = 0.0;  // even[3], odd[2] are contiguous
     for (int k = tid; k < 36; k += NT) {
       s.tphi[0][k] = cc.sphi[0][k]; s.tdx[0][k] = cc.sdx[0][k]; s.tdy[0][k] = cc.sdy[0][k];
+      s.tdxy[0][k][0] = cc.sdx[0][k]; s.tdxy[0][k][1] = cc.sdy[0][k];
     }
     if (tid < 4) s.tw[tid] = cc.w[tid];
     if (tid < 12) { s.twpsi[0][tid] = cc.wpsi[0][tid]; s.tpsi[0][tid] = cc.psi[0][tid]; }
@@ -264,7 +260,7 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
         for (int m = 0; m < 3; ++m) v += s.tpsi[q][m] * s.val[rb][cy][18 + m];
         u[U_P] = v;
         u[U_MU] = s.visc[rb][cy][q][0];
-        u[U_KAP] = s.visc[rb][cy][q][1];
+        u[U_SC] = a.js * s.tw[q] * 2.0 * a.Pr * s.visc[rb][cy][q][1];
       } else {
         const double *vv = &s.val[rb][cy][g == 0 ? 0 : (g == 1 ? 9 : 21)];
         double f0 = 0, f1 = 0, f2 = 0;
@@ -276,28 +272,6 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
         if (g == 0) { u[U_U0] = f0; u[U_G00] = f1; u[U_G10] = f2; }
         else if (g == 1) { u[U_U1] = f0; u[U_G01] = f1; u[U_G11] = f2; }
         else { u[U_T] = f0; u[U_DT0] = f1; u[U_DT1] = f2; }
-      }
-    }
-  };
-  auto state_S4 = [&](int x, int t, int nthr) {
-    const int sb = x & 1;
-    for (int k = t; k < ncol_cells * 36; k += nthr) {
-      const int cy = k / 36, r = k - cy * 36, q = r / 9, i = r - q * 9;
-      double *u = &s.uni[sb][cy * CT_UNI_C + q * CT_UNI_Q];
-      const double u0 = u[U_U0], u1 = u[U_U1], G00 = u[U_G00], G01 = u[U_G01], G10 = u[U_G10], G11 = u[U_G11];
-      const double dx = s.tdx[q][i], dy = s.tdy[q][i];
-      const double D01 = 0.5 * (G01 + G10);
-      const double S0 = G00 * dx + D01 * dy;
-      const double S1 = D01 * dx + G11 * dy;
-      const double sc = a.js * s.tw[q] * 2.0 * a.Pr * u[U_KAP];
-      double *op = &s.nod[sb][cy * CT_NOD_C + (q * 9 + i) * CT_NOD];
-      op[0] = S0; op[1] = S1; op[2] = sc * S0; op[3] = sc * S1;
-      op[4] = u0 * dx + u1 * dy;
-      if (i == 0) {
-        u[U_CONV0] = u0 * G00 + u1 * G10;
-        u[U_CONV1] = u0 * G01 + u1 * G11;
-        u[U_UDT] = u0 * u[U_DT0] + u1 * u[U_DT1];
-        u[U_DIVU] = G00 + G11;
       }
     }
   };
@@ -316,8 +290,6 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   state_S2(xs, tid, NT);
-  __syncthreads();
-  state_S4(xs, tid, NT);
   __syncthreads();
 
   int eL = 0, eR = 1, eI = 2;  // even buffers: left line, right line, idle (being written out / zeroed)
@@ -351,20 +323,22 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
     }
     double v00 = 0, v01 = 0, v10 = 0, v11 = 0, e = 0, tu0 = 0, tu1 = 0;
     const double2 *u2 = reinterpret_cast<const double2 *>(&s.uni[sb][cy * CT_UNI_C]);
-    const double *ni = &s.nod[sb][cy * CT_NOD_C + it * CT_NOD];
-    const double *nj = &s.nod[sb][cy * CT_NOD_C + jt * CT_NOD];
+    const double2 *dxy = reinterpret_cast<const double2 *>(&s.tdxy[0][0][0]);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const double2 a0 = u2[q * (CT_UNI_Q / 2) + 0], a1 = u2[q * (CT_UNI_Q / 2) + 1], a2 = u2[q * (CT_UNI_Q / 2) + 2],
-                    a3 = u2[q * (CT_UNI_Q / 2) + 3];  // (mu,G00) (G01,G10) (G11,dT0) (dT1,kap)
-      const double2 si = *reinterpret_cast<const double2 *>(ni + q * 9 * CT_NOD);
-      const double2 sj = *reinterpret_cast<const double2 *>(nj + q * 9 * CT_NOD + 2);
-      const double cj = nj[q * 9 * CT_NOD + 4];
+                    a3 = u2[q * (CT_UNI_Q / 2) + 3], a4 = u2[q * (CT_UNI_Q / 2) + 4];  // (mu,G00) (G01,G10) (G11,dT0) (dT1,sc) (u0,u1)
+      const double2 di = dxy[q * 9 + it], dj = dxy[q * 9 + jt];  // physical gradients of the test / trial shape function
       const double mu = a0.x;
       v00 = fma(mu, TA[q], v00); v11 = fma(mu, TB[q], v11); v01 = fma(mu, TC[q], v01); v10 = fma(mu, TD[q], v10);
       if (!NEWT) {
-        v00 = fma(si.x, sj.x, v00); v01 = fma(si.x, sj.y, v01); v10 = fma(si.y, sj.x, v10); v11 = fma(si.y, sj.y, v11);
+        // S_ia = sum_k D[k][a] d_k phi_i (test), S'_jb = sc * S_jb (trial)   
+        const double D01 = 0.5 * (a1.x + a1.y);
+        const double si0 = fma(a0.y, di.x, D01 * di.y), si1 = fma(D01, di.x, a2.x * di.y);
+        const double sj0 = a3.y * fma(a0.y, dj.x, D01 * dj.y), sj1 = a3.y * fma(D01, dj.x, a2.x * dj.y);
+        v00 = fma(si0, sj0, v00); v01 = fma(si0, sj1, v01); v10 = fma(si1, sj0, v10); v11 = fma(si1, sj1, v11);
       }
+      const double cj = fma(a4.x, dj.x, a4.y * dj.y);  // u . grad phi_j
       v00 = fma(TM[q], a0.y, v00);
       v01 = fma(TM[q], a1.y, v01);  // (a=0,b=1): G[1][0]
       v10 = fma(TM[q], a1.x, v10);  // (a=1,b=0): G[0][1]
@@ -475,9 +449,6 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
       // ---- state of the next column (its values were parked in shared memory one column ago)
       if (x + 1 < x1) {
         state_S2(x + 1, tid, NMT);
-        __syncwarp();
-        asm volatile("bar.sync 2, %0;" ::"n"(NMT) : "memory");  // matrix warps only
-        state_S4(x + 1, tid, NMT);
       }
     } else {
       // ---- (2) write-out of the previous column
@@ -489,13 +460,15 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const double *u = &s.uni[sb][r_cy * CT_UNI_C + q * CT_UNI_Q];
-            const double *nd = &s.nod[sb][r_cy * CT_NOD_C + (q * 9 + r_nd) * CT_NOD];
             const double w = s.tw[q];
-            const double ph = w * s.tphi[q][r_nd], dx = w * s.tdx[q][r_nd], dy = w * s.tdy[q][r_nd];
+            const double gx_ = s.tdx[q][r_nd], gy_ = s.tdy[q][r_nd];
+            const double ph = w * s.tphi[q][r_nd], dx = w * gx_, dy = w * gy_;
+            const double u0 = u[U_U0], u1 = u[U_U1], G00 = u[U_G00], G01 = u[U_G01], G10 = u[U_G10], G11 = u[U_G11];
+            const double D01 = 0.5 * (G01 + G10);
             const double m2 = 2.0 * a.Pr * w * u[U_MU], bu = a.RaPr * u[U_T];
-            r0 = fma(m2, nd[0], r0); r0 = fma(ph, u[U_CONV0] - bu * a.gx, r0); r0 = fma(-dx, u[U_P], r0);
-            r1 = fma(m2, nd[1], r1); r1 = fma(ph, u[U_CONV1] - bu * a.gy, r1); r1 = fma(-dy, u[U_P], r1);
-            r2 = fma(u[U_DT0], dx, r2); r2 = fma(u[U_DT1], dy, r2); r2 = fma(u[U_UDT], ph, r2);
+            r0 = fma(m2, fma(G00, gx_, D01 * gy_), r0); r0 = fma(ph, fma(u0, G00, u1 * G10) - bu * a.gx, r0); r0 = fma(-dx, u[U_P], r0);
+            r1 = fma(m2, fma(D01, gx_, G11 * gy_), r1); r1 = fma(ph, fma(u0, G01, u1 * G11) - bu * a.gy, r1); r1 = fma(-dy, u[U_P], r1);
+            r2 = fma(u[U_DT0], dx, r2); r2 = fma(u[U_DT1], dy, r2); r2 = fma(fma(u0, u[U_DT0], u1 * u[U_DT1]), ph, r2);
           }
         }
         __syncwarp();
@@ -510,7 +483,10 @@ __global__ void __launch_bounds__((3 * TH / 2 + 2) * 32, (TH == 8 ? 1 : 2)) k_ca
           const int cy = at / 3, p = at - cy * 3;
           double acc = 0;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) acc += s.twpsi[q][p] * s.uni[sb][cy * CT_UNI_C + q * CT_UNI_Q + U_DIVU];
+          for (int q = 0; q < 4; ++q) {
+            const double *u = &s.uni[sb][cy * CT_UNI_C + q * CT_UNI_Q];
+            acc += s.twpsi[q][p] * (u[U_G00] + u[U_G11]);
+          }
           s.odd[ob][S::ODD_P0 + cy * CT_P_BLK + CT_P_RES + p] = acc;
         }
       }
