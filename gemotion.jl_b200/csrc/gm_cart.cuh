@@ -28,9 +28,13 @@
 #include <cub/cub.cuh>
 
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
 
 #include "gm_internal.h"
 #include "gm_scatter.cuh"
+#include "gm_cart_tables.h"
 
 #define CT_XCH 64        // columns per x-chunk
 #define CT_MAXCLASS 4096
@@ -59,23 +63,11 @@
 #define CT_UNI 16                                                 // per (cell,q) uniform state
 #define CT_NOD 6                                                  // per (cell,q,node) state
 
-struct CartPairTab {  // per (test node, trial node): 27 doubles, all scaled by jac_scaling*w_q*|J|
-  double TA[4], TB[4], TC[4], TD[4], TM[4], TP[4];
-  double TK, TUT0, TUT1;
-};
-
-struct CartCell {  // constants of the P blocks (cell independent on a Cartesian mesh)
-  double UP[18][3];   // jac_scaling * sum_q w (-d_a phi_i psi_p), index a*9+i
-  double wpsi[4][3];  // w_q psi_p
-  double psi[4][3];
-  double sphi[4][9], sdx[4][9], sdy[4][9];  // physical gradients
-  double w[4];
-};
-
 struct gm_cart {
   int nclass = 0;
   int32_t *cls = nullptr;     // [ncells] rank class of each cell
   uint8_t *ctab = nullptr;    // [nclass][900]   rank[minor][major]
+  uint8_t *ptab = nullptr;    // [nclass][81][16] pair-major copy for k_gath (gm_cart_pair_ranks)
   double *visc = nullptr;     // [ncells][4][2]  (mu, kappa)
   CartPairTab *d_tab = nullptr;
   CartCell *d_cell = nullptr;
@@ -84,23 +76,6 @@ struct gm_cart {
   int th = 8;  // cell rows per strip (template parameter of k_cart)
 };
 
-struct CartArgs {
-  int nx, ny;
-  int row_begin, row_end;  // owned cell rows of the local table (ghost rows excluded)
-  const int32_t *gdofs;
-  const double *dvals;
-  const int64_t *ptr;
-  const int32_t *cls;
-  const uint8_t *ctab;
-  const double *visc;
-  const CartPairTab *tab;
-  const CartCell *cc;
-  const double *x;
-  double *nz;
-  double *b;
-  unsigned flags;
-  double Pr, RaPr, gx, gy, reg, n, js;
-};
 
 // ------------------------------------------------------------------------------------------
 // set-up kernels: rank classes + verification of the structural assumptions
@@ -221,6 +196,7 @@ __global__ void k_ct_visc(int64_t ncells, const int32_t *__restrict__ g, const d
 }
 
 #include "gm_cart_kernel.cuh"
+#include "gm_gath_kernel.cuh"
 
 // ------------------------------------------------------------------------------------------
 // host side
@@ -228,7 +204,7 @@ __global__ void k_ct_visc(int64_t ncells, const int32_t *__restrict__ g, const d
 static void gm_cart_destroy(gm_handle *h) {
   gm_cart *c = (gm_cart *)h->cart;
   if (!c) return;
-  cudaFree(c->cls); cudaFree(c->ctab); cudaFree(c->visc); cudaFree(c->d_tab); cudaFree(c->d_cell);
+  cudaFree(c->cls); cudaFree(c->ctab); cudaFree(c->ptab); cudaFree(c->visc); cudaFree(c->d_tab); cudaFree(c->d_cell);
   delete c;
   h->cart = nullptr;
 }
@@ -293,6 +269,14 @@ decided:
   }
   c->nclass = nclass;
   h->device_bytes += 4 * nc + (int64_t)nclass * 900;
+  {  // pair-major rank records for k_gath
+    std::vector<uint8_t> ct((size_t)nclass * 900), pt((size_t)nclass * 81 * 16);
+    CB(cudaMemcpy(ct.data(), c->ctab, ct.size(), cudaMemcpyDeviceToHost));
+    gm_cart_pair_ranks(nclass, ct.data(), pt.data());
+    CB(cudaMalloc(&c->ptab, pt.size()));
+    CB(cudaMemcpy(c->ptab, pt.data(), pt.size(), cudaMemcpyHostToDevice));
+    h->device_bytes += (int64_t)pt.size();
+  }
   CB(cudaMalloc(&c->visc, sizeof(double) * 8 * nc));
   CB(cudaMalloc(&c->d_tab, sizeof(CartPairTab) * 81));
   CB(cudaMalloc(&c->d_cell, sizeof(CartCell)));
@@ -319,44 +303,7 @@ static int gm_cart_tables(gm_handle *h) {
   const gm_params &p = h->prm;
   static thread_local CartPairTab tab[81];
   static thread_local CartCell cell;
-  const double detJ = k.hx * k.hy;
-  for (int q = 0; q < 4; ++q) {
-    cell.w[q] = k.w[q] * detJ;
-    for (int i = 0; i < 9; ++i) {
-      cell.sphi[q][i] = k.phi[q * 9 + i];
-      cell.sdx[q][i] = k.dphi[(q * 9 + i) * 2] / k.hx;
-      cell.sdy[q][i] = k.dphi[(q * 9 + i) * 2 + 1] / k.hy;
-    }
-    for (int m = 0; m < 3; ++m) { cell.wpsi[q][m] = cell.w[q] * k.psi[q * 3 + m]; cell.psi[q][m] = k.psi[q * 3 + m]; }
-  }
-  for (int a = 0; a < 2; ++a)
-    for (int i = 0; i < 9; ++i)
-      for (int m = 0; m < 3; ++m) {
-        double v = 0;
-        for (int q = 0; q < 4; ++q) v += cell.w[q] * (-(a == 0 ? cell.sdx[q][i] : cell.sdy[q][i]) * k.psi[q * 3 + m]);
-        cell.UP[a * 9 + i][m] = p.jac_scaling * v;
-      }
-  for (int i = 0; i < 9; ++i)
-    for (int j = 0; j < 9; ++j) {
-      CartPairTab &t = tab[i * 9 + j];
-      double kbar = 0, mbar = 0;
-      for (int q = 0; q < 4; ++q) {
-        const double w = p.jac_scaling * cell.w[q];
-        const double xi = cell.sdx[q][i], yi = cell.sdy[q][i], xj = cell.sdx[q][j], yj = cell.sdy[q][j];
-        const double K = xi * xj + yi * yj;
-        t.TA[q] = w * p.Pr * (K + xi * xj);
-        t.TB[q] = w * p.Pr * (K + yi * yj);
-        t.TC[q] = w * p.Pr * (yi * xj);  // (a=0,b=1): d_b phi_i d_a phi_j
-        t.TD[q] = w * p.Pr * (xi * yj);  // (a=1,b=0)
-        t.TM[q] = w * cell.sphi[q][i] * cell.sphi[q][j];
-        t.TP[q] = w * cell.sphi[q][i];
-        kbar += w * K;
-        mbar += w * cell.sphi[q][i] * cell.sphi[q][j];
-      }
-      t.TK = kbar;
-      t.TUT0 = -p.Ra * p.Pr * p.gx * mbar;
-      t.TUT1 = -p.Ra * p.Pr * p.gy * mbar;
-    }
+  gm_cart_fill_tables(k.w, k.phi, k.dphi, k.psi, k.hx, k.hy, p.Pr, p.Ra, p.gx, p.gy, p.jac_scaling, tab, &cell);
   GM_CUDA(cudaMemcpyAsync(c->d_tab, tab, sizeof tab, cudaMemcpyHostToDevice, h->stream));
   GM_CUDA(cudaMemcpyAsync(c->d_cell, &cell, sizeof cell, cudaMemcpyHostToDevice, h->stream));
   GM_CUDA(cudaStreamSynchronize(h->stream));  // the staging arrays are reused by the next call
@@ -383,6 +330,25 @@ static int gm_cart_launch(gm_handle *h, const CartArgs &a, bool csr, bool newt) 
   return newt ? gm_cart_launch1<TH, false, true>(h, a) : gm_cart_launch1<TH, false, false>(h, a);
 }
 
+// ---- k_gath (gm_gath_kernel.cuh): NG trios of matrix warps + GA_NAUX aux warps, one CTA per SM
+template <int NG, bool CSR, bool NEWT>
+static int gm_gath_launch1(gm_handle *h, const CartArgs &a) {
+  static bool attr_set = false;
+  const size_t sm = sizeof(GaSmem<NG>);
+  if (!attr_set) {
+    GM_CUDA(cudaFuncSetAttribute(k_gath<NG, CSR, NEWT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    attr_set = true;
+  }
+  dim3 grid((a.nx + 1 + GA_XCH - 1) / GA_XCH, (a.row_end - a.row_begin + 1 + 4 * NG - 1) / (4 * NG));
+  k_gath<NG, CSR, NEWT><<<grid, (3 * NG + GA_NAUX) * 32, sm, h->stream>>>(a);
+  return GM_OK;
+}
+template <int NG>
+static int gm_gath_launch(gm_handle *h, const CartArgs &a, bool csr, bool newt) {
+  if (csr) return newt ? gm_gath_launch1<NG, true, true>(h, a) : gm_gath_launch1<NG, true, false>(h, a);
+  return newt ? gm_gath_launch1<NG, false, true>(h, a) : gm_gath_launch1<NG, false, false>(h, a);
+}
+
 static int gm_cart_run(gm_handle *h, const double *d_x, double *d_nz, double *d_b, unsigned flags, int64_t *launches) {
   gm_cart *c = (gm_cart *)h->cart;
   int rc = gm_cart_tables(h);
@@ -391,7 +357,7 @@ static int gm_cart_run(gm_handle *h, const double *d_x, double *d_nz, double *d_
   CartArgs a;
   a.nx = h->d.nx; a.ny = h->d.ny;
   a.row_begin = h->d.ghost_lo; a.row_end = h->d.ny - h->d.ghost_hi;
-  a.gdofs = h->gdofs; a.dvals = h->dvals; a.ptr = h->ptr; a.cls = c->cls; a.ctab = c->ctab; a.visc = c->visc;
+  a.gdofs = h->gdofs; a.dvals = h->dvals; a.ptr = h->ptr; a.cls = c->cls; a.ctab = c->ctab; a.ptab = c->ptab; a.visc = c->visc;
   a.tab = c->d_tab; a.cc = c->d_cell; a.x = d_x; a.nz = d_nz; a.b = d_b; a.flags = flags;
   a.Pr = p.Pr; a.RaPr = p.Ra * p.Pr; a.gx = p.gx; a.gy = p.gy; a.reg = p.reg; a.n = p.n; a.js = p.jac_scaling;
   const bool newt = p.n == 1.0;
@@ -400,7 +366,11 @@ static int gm_cart_run(gm_handle *h, const double *d_x, double *d_nz, double *d_
     ++*launches;
   }
   const bool csr = h->d.layout == GM_LAYOUT_CSR;
-  rc = gm_cart_launch<4>(h, a, csr, newt);
+  // GM_CART_KERNEL=sweep selects the first-generation kernel (k_cart) for A/B measurements
+  static const bool use_sweep = [] { const char *e = getenv("GM_CART_KERNEL"); return e && strcmp(e, "sweep") == 0; }();
+  static const int gath_ng = [] { const char *e = getenv("GM_GATH_NG"); return e ? atoi(e) : 2; }();
+  if (use_sweep) rc = gm_cart_launch<4>(h, a, csr, newt);
+  else rc = gath_ng == 1 ? gm_gath_launch<1>(h, a, csr, newt) : gm_gath_launch<2>(h, a, csr, newt);
   if (rc) return rc;
   ++*launches;
   GM_CUDA(cudaGetLastError());

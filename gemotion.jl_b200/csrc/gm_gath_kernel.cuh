@@ -1,0 +1,558 @@
+// gm_gath_kernel.cuh -- structured path, second generation: register gather ("owner lane computes its
+// nnz entries completely").  Same reference interface as gm_cart_kernel.cuh (jacobian!/residual! of the
+// operator built at /root/reference/src/Solver.jl:157, integrands Solver.jl:111-152, arithmetic SURVEY A.4).
+//
+// k_cart (gm_cart_kernel.cuh) accumulates the 837 entries of every cell matrix into shared-memory lists by
+// read-modify-write; ncu shows it bound by shared-memory wavefronts (855 per cell).  Here a lane owns an
+// OUTPUT node pair (A = list owner, B = neighbour) and sums the contributions of the 1, 2 or 4 cells that
+// contain both nodes in registers; every list position is then stored to shared memory exactly once (no
+// read-modify-write, no zeroing) and each completed list leaves with one TMA bulk copy.
+//
+//  * Mirror trick: on a Cartesian mesh the reference-element products of the local pair (i,j) of the cell
+//    left of / below a node equal those of the mirrored pair of the cell right of / above it, with the
+//    quadrature points permuted and sign flips on odd x/y derivative counts.  The flips are moved into the
+//    per-cell STATE, of which four variants (I, X, Y, XY) are kept in shared memory: variant m stores at
+//    slot q the fields of the actual point q^m, with G01, G10, D01 multiplied by sx*sy and (u0,u1) by
+//    (sx,sy).  A lane therefore keeps ONE set of 43 table values in registers and evaluates any of its
+//    cells with the same instruction stream; only v01, v10 need the sign sx*sy when they are merged.
+//  * Work unit: a "quad" = the four nodes (V vertex, H bottom-edge, E left-edge, C centre) at the lower left
+//    of a cell.  Four vertically adjacent quads = 64 output node pairs x 9 entries = 81 cell-pair
+//    evaluations per cell = 81 lanes x 4 rounds: V lanes (36) evaluate their 4 cells, E / H lanes (18 + 18)
+//    two quads x two cells, C lanes (9) four quads x one cell.  A trio of warps (27 lanes each) runs 4
+//    identical rounds per column; consecutive rounds that hit the same output are merged before the store.
+//  * CTA = NG trios + 2 aux warps, sweeping a strip of 4*NG quad rows column by column.  Aux warps: state
+//    of column X+1 (fields at the quadrature points, four variants), the constant P-block entries, the
+//    residual (written straight to b), list bases of column X+1 (cp.async), TMA write-out of column X-1.
+//    One CTA barrier per column.
+//
+// The file compiles for the device (nvcc, sm_100a) and -- with GM_EMU -- as host C++ under
+// tests/emu/cuda_emu.h, which runs every CUDA thread as a pthread; that build exists only so that the
+// index logic can be checked against the oracle without a GPU (tests/test_gath_emu.py).
+#pragma once
+
+#define GA_XCH 128                 // quad columns per x-chunk
+#define GA_NAUX 4                  // aux warps
+#define GA_QS 12                   // doubles per (variant, point) state record
+#define GA_VS 56                   // doubles per variant: 4 records + 8 (p, T of the 4 points; variant 0 only)
+#define GA_CS (4 * GA_VS + 2)      // doubles per cell (226: consecutive cell rows are shifted by 16 B in the banks)
+#define GA_QSTRIDE 708             // staged doubles per quad: 15 list slots (704) + bank shift
+
+// state record layout (doubles): (mu,G00) (G01,G10) (G11,D01) (dT0,dT1) (sc,u0) (u1,-)
+#define GS_MU 0
+#define GS_G00 1
+#define GS_G01 2
+#define GS_G10 3
+#define GS_G11 4
+#define GS_D01 5
+#define GS_DT0 6
+#define GS_DT1 7
+#define GS_SC 8
+#define GS_U0 9
+#define GS_U1 10
+
+#ifdef GM_EMU
+#define GA_LDG(p) (*(p))
+#else
+#define GA_LDG(p) __ldg(p)
+__device__ __forceinline__ void ga_cp_async(void *sdst, const void *gsrc, int bytes);
+#endif
+
+// ---- asynchronous copies (device: LDGSTS / UBLKCP; emulation: deferred memcpy, see cuda_emu.h)
+#ifndef GM_EMU
+__device__ __forceinline__ void ga_cp4(void *sdst, const void *gsrc) {
+  const uint32_t sa = (uint32_t)__cvta_generic_to_shared(sdst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void ga_cp8(void *sdst, const void *gsrc) {
+  const uint32_t sa = (uint32_t)__cvta_generic_to_shared(sdst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void ga_cp16(void *sdst, const void *gsrc) {
+  const uint32_t sa = (uint32_t)__cvta_generic_to_shared(sdst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void ga_cp_wait_all() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void ga_bulk_store(double *gdst, const double *ssrc, int bytes) {
+  const uint32_t sa = (uint32_t)__cvta_generic_to_shared(ssrc);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(sa), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ga_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void ga_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void ga_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void ga_bar_aux() { asm volatile("bar.sync 2, %0;" ::"n"(GA_NAUX * 32) : "memory"); }
+#endif
+
+// local node index of the tensor position (ix, iy) of a Q2 cell (same table as c_ct_node)
+__host__ __device__ __forceinline__ int ga_node(int ix, int iy) {
+  return (0x352786140ull >> (4 * (iy * 3 + ix))) & 15;  // {0,4,1, 6,8,7, 2,5,3}
+}
+
+// Role of trio lane t (0..80): list-owner node type A (0 V, 1 H, 2 E, 3 C), neighbour position (bx, by) in
+// the canonical (upper right) cell, and four rounds: quad of the group, state variant m = mx + 2 my (the
+// evaluated cell is (X - mx, Y - my)), flush flag (the next round belongs to another output).
+struct GaRole {
+  int A, bx, by;
+  int gq[4], m[4], flush[4];
+};
+__host__ __device__ inline GaRole ga_role(int t) {
+  GaRole r;
+  int j;
+  if (t < 36) {            // V: one quad, its four cells
+    r.A = 0; j = t % 9;
+    const int g = t / 9;
+    r.bx = j % 3; r.by = j / 3;
+    const bool yfirst = r.bx > 0 && r.by == 0;  // outputs (I,Y) and (X,XY) coincide: keep them adjacent
+    for (int k = 0; k < 4; ++k) { r.gq[k] = g; r.m[k] = yfirst ? ((k & 1) * 2 + (k >> 1)) : k; }
+  } else if (t < 72) {     // E (left edge): cells I, X;  H (bottom edge): cells I, Y;  two quads each
+    const bool isE = t < 54;
+    const int u = isE ? t - 36 : t - 54, h = u / 9;
+    j = u % 9;
+    r.A = isE ? 2 : 1;
+    r.bx = j % 3; r.by = j / 3;
+    for (int k = 0; k < 4; ++k) { r.gq[k] = 2 * h + (k >> 1); r.m[k] = (k & 1) ? (isE ? 1 : 2) : 0; }
+  } else {                 // C: four quads, own cell
+    j = t - 72;
+    r.A = 3; r.bx = j % 3; r.by = j / 3;
+    for (int k = 0; k < 4; ++k) { r.gq[k] = k; r.m[k] = 0; }
+  }
+  for (int k = 0; k < 4; ++k) {
+    if (k == 3 || r.gq[k + 1] != r.gq[k]) { r.flush[k] = 1; continue; }
+    const int m0 = r.m[k], m1 = r.m[k + 1];
+    const int ox0 = (m0 & 1) ? -r.bx : r.bx, oy0 = (m0 & 2) ? -r.by : r.by;
+    const int ox1 = (m1 & 1) ? -r.bx : r.bx, oy1 = (m1 & 2) ? -r.by : r.by;
+    r.flush[k] = (ox0 != ox1 || oy0 != oy1) ? 1 : 0;
+  }
+  return r;
+}
+__host__ __device__ __forceinline__ int ga_ax(int A) { return (A == 1 || A == 3) ? 1 : 0; }
+__host__ __device__ __forceinline__ int ga_ay(int A) { return (A >= 2) ? 1 : 0; }
+// cells (variants) that contain node type A:  V: I X Y XY,  H: I Y,  E: I X,  C: I
+__host__ __device__ __forceinline__ int ga_nvar(int A) { return A == 0 ? 4 : (A == 3 ? 1 : 2); }
+__host__ __device__ __forceinline__ int ga_var(int A, int s) { return A == 0 ? s : (A == 1 ? 2 * s : (A == 2 ? s : 0)); }
+// local node of node type A inside the cell of variant m
+__host__ __device__ __forceinline__ int ga_anode(int A, int m) {
+  const int ax = ga_ax(A), ay = ga_ay(A);
+  return ga_node((m & 1) ? 2 - ax : ax, (m & 2) ? 2 - ay : ay);
+}
+
+template <int NG>
+struct GaSmem {
+  static constexpr int QH = 4 * NG, NR = QH + 1;
+  double st[3][NR * GA_CS];          // state ring (cell column mod 3)
+  double stage[2][QH * GA_QSTRIDE];  // staged lists of quad column X (X & 1)
+  double val[4][NR][30];             // iterate values of cell column c (c & 3)
+  double visc[4][NR][4][2];
+  long long lbase[4][QH][16];        // list bases / ends of quad column X (X & 3); 15 used
+  long long lnext[4][QH][16];
+  double respart[QH][16][3];         // residual partial sums [quad row][A*4 + cell][k]
+  double tphi[4][9], tdx[4][9], tdy[4][9], tw[4], twpsi[4][3], tpsi[4][3];
+  double UP[18][3];
+  int32_t gd[8][NR][30];             // dof ids of cell column c (c & 7)
+  int32_t lg[4][QH][16];             // dof id of each list of quad column X (0: no list / not assembled here)
+  int32_t cls[4][NR];
+  int16_t slot[16];
+  uint8_t pu[54][4];                 // (A, m, a, p) of the 54 P-row entries of a quad's U lists
+};
+
+template <int NG, bool CSR, bool NEWT>
+__global__ void __launch_bounds__((3 * NG + GA_NAUX) * 32, 1) k_gath(CartArgs a) {
+  using S = GaSmem<NG>;
+  constexpr int QH = S::QH, NR = S::NR;
+  constexpr int NMW = 3 * NG, NMT = NMW * 32, NAT = GA_NAUX * 32, NT = NMT + NAT;
+#ifdef GM_EMU
+  unsigned char *smem_raw = emu_smem();
+#else
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+#endif
+  S &s = *reinterpret_cast<S *>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool is_aux = warp >= NMW;
+  const int at = tid - NMT;  // aux thread index
+  const int Yq0 = a.row_begin + (int)blockIdx.y * QH;     // first quad row of the strip
+  const int nqr = min(QH, a.row_end + 1 - Yq0);           // quad rows Yq0 .. Yq0+nqr-1 (row_end = the top mesh line)
+  const int Yc0 = Yq0 - 1;                                // cell row of state row 0
+  const int X0 = (int)blockIdx.x * GA_XCH, X1 = min(a.nx + 1, X0 + GA_XCH);
+  const bool jac = (a.flags & GM_JACOBIAN) != 0, res = (a.flags & GM_RESIDUAL) != 0;
+  const CartCell &cc = *a.cc;
+
+  auto row_in_table = [&](int rr) { const int cy = Yc0 + rr; return rr >= 0 && rr <= nqr && cy >= 0 && cy < a.ny; };
+  auto row_owned = [&](int rr) { const int cy = Yc0 + rr; return rr >= 0 && rr <= nqr && cy >= a.row_begin && cy < a.row_end; };
+  auto col_ok = [&](int c) { return c >= 0 && c < a.nx; };
+
+  // ---- constant tables
+  for (int k = tid; k < 36; k += NT) { s.tphi[0][k] = cc.sphi[0][k]; s.tdx[0][k] = cc.sdx[0][k]; s.tdy[0][k] = cc.sdy[0][k]; }
+  if (tid < 4) s.tw[tid] = cc.w[tid];
+  if (tid < 12) { s.twpsi[0][tid] = cc.wpsi[0][tid]; s.tpsi[0][tid] = cc.psi[0][tid]; }
+  for (int k = tid; k < 54; k += NT) s.UP[0][k] = cc.UP[0][k];
+  if (tid == 0) {
+    const int16_t sl[16] = {0, 88, 176, 252, 304, 356, 402, 454, 506, 552, 584, 616, 644, 664, 684, 704};
+    for (int k = 0; k < 16; ++k) s.slot[k] = sl[k];
+    int n = 0;
+    for (int A = 0; A < 4; ++A)
+      for (int sv = 0; sv < ga_nvar(A); ++sv)
+        for (int c2 = 0; c2 < 2; ++c2)
+          for (int p = 0; p < 3; ++p) {
+            s.pu[n][0] = (uint8_t)A; s.pu[n][1] = (uint8_t)ga_var(A, sv); s.pu[n][2] = (uint8_t)c2; s.pu[n][3] = (uint8_t)p;
+            ++n;
+          }
+  }
+
+  // ---- role of a matrix lane
+  const int grp = is_aux ? 0 : warp / 3, wl = warp % 3;
+  const bool lane_on = !is_aux && lane < 27;
+  const GaRole role = ga_role(lane_on ? wl * 27 + lane : 0);
+  const int A = role.A;
+  uint32_t R[4];  // per round: [0:3] state row, [4:5] variant, [6] flush, [7:10] quad row, [11:17] pair index, [18] in table, [19] owned
+  {
+    const int ax = ga_ax(A), ay = ga_ay(A);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int m = role.m[r], mx = m & 1, my = m >> 1;
+      const int rowq = grp * 4 + role.gq[r], rr = rowq + 1 - my;
+      const bool rq_ok = lane_on && rowq < nqr;
+      const int Mact = ga_node(mx ? 2 - ax : ax, my ? 2 - ay : ay);
+      const int mact = ga_node(mx ? 2 - role.bx : role.bx, my ? 2 - role.by : role.by);
+      R[r] = (uint32_t)rr | ((uint32_t)m << 4) | ((uint32_t)role.flush[r] << 6) | ((uint32_t)rowq << 7) |
+             ((uint32_t)(Mact * 9 + mact) << 11) | ((rq_ok && row_in_table(rr)) ? (1u << 18) : 0u) |
+             ((rq_ok && row_owned(rr)) ? (1u << 19) : 0u);
+    }
+  }
+  // reference-element products of the canonical pair (test node it, trial node jt)
+  const int nA = ga_node(ga_ax(A), ga_ay(A)), nB = ga_node(role.bx, role.by);
+  const int it = CSR ? nA : nB, jt = CSR ? nB : nA;
+  double TA[4], TB[4], TC[4], TD[4], TM[4], TP[4], TK, TUT0, TUT1;
+  double dix[4], diy[4], djx[4], djy[4];
+  {
+    const CartPairTab &t = a.tab[it * 9 + jt];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      TA[q] = t.TA[q]; TB[q] = t.TB[q]; TC[q] = t.TC[q]; TD[q] = t.TD[q]; TM[q] = t.TM[q]; TP[q] = t.TP[q];
+      dix[q] = cc.sdx[q][it]; diy[q] = cc.sdy[q][it]; djx[q] = cc.sdx[q][jt]; djy[q] = cc.sdy[q][jt];
+    }
+    TK = t.TK; TUT0 = t.TUT0; TUT1 = t.TUT1;
+  }
+  const int slotA0 = A == 0 ? 0 : (A == 1 ? 252 : (A == 2 ? 402 : 552));
+  const int slotA1 = slotA0 + (A == 0 ? 88 : (A == 3 ? 32 : 52));
+  const int slotA2 = slotA1 + (A == 0 ? 88 : (A == 3 ? 32 : 52));
+
+  __syncthreads();
+
+  // =====================================================================================
+  // aux tasks
+  // =====================================================================================
+  // (A1) dof ids of cell column c
+  auto issue_gd = [&](int c) {
+    if (!col_ok(c)) return;
+    for (int k = at; k < NR * 30; k += NAT) {
+      const int rr = k / 30, l = k - rr * 30;
+      if (!row_in_table(rr)) continue;
+      ga_cp4(&s.gd[c & 7][rr][l], a.gdofs + ((int64_t)(Yc0 + rr) * a.nx + c) * 30 + l);
+    }
+  };
+  // (A2) iterate values, viscosity, rank class of cell column c (its dof ids have landed)
+  auto issue_val = [&](int c) {
+    if (!col_ok(c)) return;
+    for (int k = at; k < NR * 30; k += NAT) {
+      const int rr = k / 30, l = k - rr * 30;
+      if (!row_in_table(rr)) continue;
+      const int32_t d = s.gd[c & 7][rr][l];
+      ga_cp8(&s.val[c & 3][rr][l], d > 0 ? a.x + (d - 1) : a.dvals + (-d - 1));
+    }
+    for (int k = at; k < NR * 4; k += NAT) {
+      const int rr = k >> 2, q = k & 3;
+      if (!row_in_table(rr)) continue;
+      const int64_t cell = (int64_t)(Yc0 + rr) * a.nx + c;
+      if (!NEWT) ga_cp16(&s.visc[c & 3][rr][q][0], a.visc + (cell * 4 + q) * 2);
+      if (q == 0) ga_cp4(&s.cls[c & 3][rr], a.cls + cell);
+    }
+  };
+  // (A3) state of cell column c: fields at the quadrature points, four mirror variants
+  auto state = [&](int c) {
+    if (!col_ok(c)) return;
+    double *sc0 = s.st[c % 3];
+    for (int k = at; k < NR * 12; k += NAT) {
+      const int rr = k / 12, e = k - rr * 12, q = e & 3, g = e >> 2;
+      if (!row_owned(rr)) continue;
+      double *cs = sc0 + rr * GA_CS;
+      const double *vv = &s.val[c & 3][rr][0];
+      if (g == 0) {         // velocity
+        double u0 = 0, u1 = 0, G00 = 0, G01 = 0, G10 = 0, G11 = 0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+          const double ph = s.tphi[q][i], dx = s.tdx[q][i], dy = s.tdy[q][i], ux = vv[i], uy = vv[9 + i];
+          u0 = fma(ph, ux, u0); G00 = fma(dx, ux, G00); G10 = fma(dy, ux, G10);
+          u1 = fma(ph, uy, u1); G01 = fma(dx, uy, G01); G11 = fma(dy, uy, G11);
+        }
+        const double D01 = 0.5 * (G01 + G10);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const double sx = (m & 1) ? -1.0 : 1.0, sy = (m & 2) ? -1.0 : 1.0, sxy = sx * sy;
+          double *o = cs + m * GA_VS + (q ^ m) * GA_QS;
+          o[GS_G00] = G00; o[GS_G01] = sxy * G01; o[GS_G10] = sxy * G10; o[GS_G11] = G11; o[GS_D01] = sxy * D01;
+          o[GS_U0] = sx * u0; o[GS_U1] = sy * u1;
+        }
+      } else if (g == 1) {  // temperature
+        double T = 0, d0 = 0, d1 = 0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+          const double tv = vv[21 + i];
+          T = fma(s.tphi[q][i], tv, T); d0 = fma(s.tdx[q][i], tv, d0); d1 = fma(s.tdy[q][i], tv, d1);
+        }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          double *o = cs + m * GA_VS + (q ^ m) * GA_QS;
+          o[GS_DT0] = d0; o[GS_DT1] = d1;
+        }
+        cs[4 * GA_QS + 2 * q + 1] = T;
+      } else {              // pressure, viscosity
+        double p = 0;
+#pragma unroll
+        for (int m = 0; m < 3; ++m) p += s.tpsi[q][m] * vv[18 + m];
+        const double mu = NEWT ? 1.0 : s.visc[c & 3][rr][q][0];
+        const double sc = NEWT ? 0.0 : a.js * s.tw[q] * 2.0 * a.Pr * s.visc[c & 3][rr][q][1];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          double *o = cs + m * GA_VS + (q ^ m) * GA_QS;
+          o[GS_MU] = mu; o[GS_SC] = sc;
+        }
+        cs[4 * GA_QS + 2 * q] = p;
+      }
+    }
+  };
+  // (A4) list records of quad column c: dof id, then (cp.async) list base and end
+  auto issue_lists = [&](int c) {
+    for (int k = at; k < QH * 15; k += NAT) {
+      const int rowq = k / 15, li = k - rowq * 15;
+      int32_t g = 0;
+      bool active = false;
+      if (rowq < nqr) {
+        if (li < 12) {
+          const int An = li / 3, kk = li - An * 3;
+          bool found = false;
+          for (int sv = 0; sv < ga_nvar(An); ++sv) {
+            const int m = ga_var(An, sv), cx = c - (m & 1), rr = rowq + 1 - (m >> 1);
+            if (!col_ok(cx) || !row_in_table(rr)) continue;
+            if (row_owned(rr)) active = true;
+            if (!found) {
+              found = true;
+              const int nd = ga_anode(An, m);
+              g = s.gd[cx & 7][rr][kk == 0 ? nd : (kk == 1 ? 9 + nd : 21 + nd)];
+            }
+          }
+        } else if (col_ok(c) && row_owned(rowq + 1)) {
+          active = true;
+          g = s.gd[c & 7][rowq + 1][18 + (li - 12)];
+        }
+      }
+      if (!active || g < 0) g = 0;
+      s.lg[c & 3][rowq][li] = g;
+      if (g > 0) {
+        ga_cp8(&s.lbase[c & 3][rowq][li], a.ptr + (g - 1));
+        ga_cp8(&s.lnext[c & 3][rowq][li], a.ptr + g);
+      } else {
+        s.lbase[c & 3][rowq][li] = 0; s.lnext[c & 3][rowq][li] = 0;
+      }
+    }
+  };
+  // (A5) constant P-block entries of quad column X -> staged lists
+  auto p_entries = [&](int X) {
+    double *stg0 = s.stage[X & 1];
+    for (int k = at; k < QH * 108; k += NAT) {
+      const int rowq = k / 108, e = k - rowq * 108;
+      if (rowq >= nqr) break;
+      int li, rkidx, upi, upp;
+      bool owned;
+      int cx, rr;
+      double sgn;
+      if (e < 54) {      // P rows (CSC) / P columns (CSR) inside the U lists of node A
+        const int An = s.pu[e][0], m = s.pu[e][1], c2 = s.pu[e][2], p = s.pu[e][3];
+        cx = X - (m & 1); rr = rowq + 1 - (m >> 1);
+        const int nd = ga_anode(An, m);
+        li = An * 3 + c2; upi = c2 * 9 + nd; upp = p;
+        rkidx = (18 + p) * 30 + upi;
+        sgn = CSR ? 1.0 : -1.0;
+      } else {           // the three P lists of the cell of this quad
+        const int p = (e - 54) / 18, ud = (e - 54) - p * 18;
+        cx = X; rr = rowq + 1;
+        li = 12 + p; upi = ud; upp = p;
+        rkidx = ud * 30 + 18 + p;
+        sgn = CSR ? -1.0 : 1.0;
+      }
+      if (!col_ok(cx) || !row_in_table(rr)) continue;
+      owned = row_owned(rr);
+      if (e >= 54 && !owned) continue;
+      const int rk = GA_LDG(a.ctab + (int64_t)s.cls[cx & 3][rr] * 900 + rkidx);
+      if (rk == 0xFF) continue;
+      const int par = (int)(s.lbase[X & 3][rowq][li] & 1);
+      stg0[rowq * GA_QSTRIDE + s.slot[li] + par + rk] = owned ? sgn * s.UP[upi][upp] : 0.0;
+    }
+  };
+  // (A6) residual of the dofs of quad column X: partial sums per (node, cell), then one store per dof
+  auto residual = [&](int X) {
+    for (int k = at; k < QH * 16; k += NAT) {
+      const int rowq = k >> 4, An = (k >> 2) & 3, sv = k & 3;
+      double r0 = 0, r1 = 0, r2 = 0;
+      if (rowq < nqr && sv < ga_nvar(An)) {
+        const int m = ga_var(An, sv), cx = X - (m & 1), rr = rowq + 1 - (m >> 1);
+        if (col_ok(cx) && row_owned(rr)) {
+          const int nd = ga_anode(An, m);
+          const double *cs = s.st[cx % 3] + rr * GA_CS;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const double *u = cs + q * GA_QS;
+            const double w = s.tw[q], gx_ = s.tdx[q][nd], gy_ = s.tdy[q][nd];
+            const double ph = w * s.tphi[q][nd], dx = w * gx_, dy = w * gy_;
+            const double u0 = u[GS_U0], u1 = u[GS_U1], G00 = u[GS_G00], G01 = u[GS_G01], G10 = u[GS_G10], G11 = u[GS_G11];
+            const double D01 = u[GS_D01], pq = cs[4 * GA_QS + 2 * q], Tq = cs[4 * GA_QS + 2 * q + 1];
+            const double m2 = 2.0 * a.Pr * w * u[GS_MU], bu = a.RaPr * Tq;
+            r0 = fma(m2, fma(G00, gx_, D01 * gy_), r0); r0 = fma(ph, fma(u0, G00, u1 * G10) - bu * a.gx, r0); r0 = fma(-dx, pq, r0);
+            r1 = fma(m2, fma(D01, gx_, G11 * gy_), r1); r1 = fma(ph, fma(u0, G01, u1 * G11) - bu * a.gy, r1); r1 = fma(-dy, pq, r1);
+            r2 = fma(u[GS_DT0], dx, r2); r2 = fma(u[GS_DT1], dy, r2); r2 = fma(fma(u0, u[GS_DT0], u1 * u[GS_DT1]), ph, r2);
+          }
+        }
+      }
+      s.respart[rowq][k & 15][0] = r0; s.respart[rowq][k & 15][1] = r1; s.respart[rowq][k & 15][2] = r2;
+    }
+    ga_bar_aux();
+    for (int k = at; k < QH * 15; k += NAT) {
+      const int rowq = k / 15, li = k - rowq * 15;
+      if (rowq >= nqr) break;
+      const int32_t g = s.lg[X & 3][rowq][li];
+      if (g <= 0) continue;
+      double v;
+      if (li < 12) {
+        const int An = li / 3, kk = li - An * 3;
+        v = (s.respart[rowq][An * 4][kk] + s.respart[rowq][An * 4 + 1][kk]) + (s.respart[rowq][An * 4 + 2][kk] + s.respart[rowq][An * 4 + 3][kk]);
+      } else {
+        const int p = li - 12;
+        const double *cs = s.st[X % 3] + (rowq + 1) * GA_CS;
+        v = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v += s.twpsi[q][p] * (cs[q * GA_QS + GS_G00] + cs[q * GA_QS + GS_G11]);
+      }
+      a.b[g - 1] = v;
+    }
+    ga_bar_aux();  // respart is reused by the next column
+  };
+  // (A7) write-out of quad column X: one TMA bulk copy per completed list
+  auto write_out = [&](int X) {
+    ga_fence_async();
+    const double *stg0 = s.stage[X & 1];
+    for (int k = at; k < QH * 15; k += NAT) {
+      const int rowq = k / 15, li = k - rowq * 15;
+      if (rowq >= nqr) break;
+      if (s.lg[X & 3][rowq][li] <= 0) continue;
+      const long long base = s.lbase[X & 3][rowq][li];
+      const int len = (int)(s.lnext[X & 3][rowq][li] - base);
+      const int par = (int)(base & 1);
+      const double *src = stg0 + rowq * GA_QSTRIDE + s.slot[li] + par;  // element k of the list lives at src[k]
+      double *dst = a.nz + base;
+      int k0 = 0, n = len;
+      if (par) { dst[0] = src[0]; k0 = 1; n -= 1; }
+      if (n & 1) { dst[k0 + n - 1] = src[k0 + n - 1]; n -= 1; }
+      if (n > 0) ga_bulk_store(dst + k0, src + k0, n * 8);
+    }
+    ga_bulk_commit();
+  };
+
+  // =====================================================================================
+  // column sweep.  Step X (matrix: quad column X): aux prepares dof ids of X+3, values of X+2, state and
+  // list records of X+1.  Four warm-up steps fill the pipeline.
+  // =====================================================================================
+  for (int X = X0 - 4; X < X1; ++X) {
+    const bool live = X >= X0;
+    if (is_aux) {
+      if (live && X > X0 && jac) write_out(X - 1);
+      issue_gd(X + 3);
+      issue_val(X + 2);
+      if (X + 1 >= X0 && X + 1 < X1) issue_lists(X + 1);
+      if (live && jac) p_entries(X);
+      if (live && res) residual(X);
+      state(X + 1);
+      ga_cp_wait_all();
+      ga_bulk_wait_read();
+      ga_fence_async();
+    } else if (live && jac) {
+      const double *stc0 = s.st[X % 3], *stc1 = s.st[(X + 2) % 3];  // cell columns X and X-1
+      double *stg0 = s.stage[X & 1];
+      double v00 = 0, v01 = 0, v10 = 0, v11 = 0, tu0 = 0, tu1 = 0, tt = 0, ut0 = 0, ut1 = 0;
+      uint32_t rk0 = 0, rk1 = 0, rk2 = 0;
+      bool have = false;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const uint32_t info = R[r];
+        const int rr = info & 15, m = (info >> 4) & 3, mx = m & 1;
+        const int cx = X - mx;
+        const bool cok = cx >= 0 && cx < a.nx;
+        if (cok && (info & (1u << 18))) {
+          const uint4 rec = GA_LDG(reinterpret_cast<const uint4 *>(a.ptab) + ((int64_t)s.cls[cx & 3][rr] * 81 + ((info >> 11) & 127)));
+          rk0 = rec.x; rk1 = rec.y; rk2 = rec.z;
+          have = true;
+        }
+        if (cok && (info & (1u << 19))) {
+          const double2 *sp = reinterpret_cast<const double2 *>((mx ? stc1 : stc0) + rr * GA_CS + m * GA_VS);
+          const double sg = (m == 1 || m == 2) ? -1.0 : 1.0;
+          double w00 = 0, w01 = 0, w10 = 0, w11 = 0, e = 0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const double2 a0 = sp[q * 6 + 0], a1 = sp[q * 6 + 1], a2 = sp[q * 6 + 2], a3 = sp[q * 6 + 3], a4 = sp[q * 6 + 4],
+                          a5 = sp[q * 6 + 5];  // (mu,G00) (G01,G10) (G11,D01) (dT0,dT1) (sc,u0) (u1,-)
+            const double mu = a0.x;
+            w00 = fma(mu, TA[q], w00); w11 = fma(mu, TB[q], w11); w01 = fma(mu, TC[q], w01); w10 = fma(mu, TD[q], w10);
+            if (!NEWT) {
+              // S_ia = sum_k D[k][a] d_k phi_i (test), S'_jb = sc * S_jb (trial)   
+              const double D01 = a2.y;
+              const double si0 = fma(a0.y, dix[q], D01 * diy[q]), si1 = fma(D01, dix[q], a2.x * diy[q]);
+              const double sj0 = a4.x * fma(a0.y, djx[q], D01 * djy[q]), sj1 = a4.x * fma(D01, djx[q], a2.x * djy[q]);
+              w00 = fma(si0, sj0, w00); w01 = fma(si0, sj1, w01); w10 = fma(si1, sj0, w10); w11 = fma(si1, sj1, w11);
+            }
+            const double cj = fma(a4.y, djx[q], a5.x * djy[q]);  // u . grad phi_j
+            w00 = fma(TM[q], a0.y, w00);
+            w01 = fma(TM[q], a1.y, w01);  // (a=0,b=1): G[1][0]
+            w10 = fma(TM[q], a1.x, w10);  // (a=1,b=0): G[0][1]
+            w11 = fma(TM[q], a2.x, w11);
+            e = fma(TP[q], cj, e);
+            tu0 = fma(TM[q], a3.x, tu0);
+            tu1 = fma(TM[q], a3.y, tu1);
+          }
+          v00 += w00 + e; v11 += w11 + e;
+          v01 = fma(sg, w01, v01); v10 = fma(sg, w10, v10);
+          tt += TK + e; ut0 += TUT0; ut1 += TUT1;
+        }
+        if (info & (1u << 6)) {
+          if (have) {
+            const int rowq = (info >> 7) & 15;
+            double *q0 = stg0 + rowq * GA_QSTRIDE;
+            const int *lb = reinterpret_cast<const int *>(&s.lbase[X & 3][rowq][A * 3]);
+            double *b0 = q0 + slotA0 + (lb[0] & 1), *b1 = q0 + slotA1 + (lb[2] & 1), *b2 = q0 + slotA2 + (lb[4] & 1);
+            double e00, e01, e02, e10, e11, e12, e20, e21, e22;  // [list k][minor dof l]
+            if (CSR) { e00 = v00; e01 = v01; e02 = ut0; e10 = v10; e11 = v11; e12 = ut1; e20 = tu0; e21 = tu1; e22 = tt; }
+            else     { e00 = v00; e01 = v10; e02 = tu0; e10 = v01; e11 = v11; e12 = tu1; e20 = ut0; e21 = ut1; e22 = tt; }
+            int rk;
+            rk = rk0 & 255;         if (rk != 255) b0[rk] = e00;
+            rk = (rk0 >> 8) & 255;  if (rk != 255) b0[rk] = e01;
+            rk = (rk0 >> 16) & 255; if (rk != 255) b0[rk] = e02;
+            rk = rk0 >> 24;         if (rk != 255) b1[rk] = e10;
+            rk = rk1 & 255;         if (rk != 255) b1[rk] = e11;
+            rk = (rk1 >> 8) & 255;  if (rk != 255) b1[rk] = e12;
+            rk = (rk1 >> 16) & 255; if (rk != 255) b2[rk] = e20;
+            rk = rk1 >> 24;         if (rk != 255) b2[rk] = e21;
+            rk = rk2 & 255;         if (rk != 255) b2[rk] = e22;
+          }
+          v00 = v01 = v10 = v11 = tu0 = tu1 = tt = ut0 = ut1 = 0;
+          have = false;
+        }
+      }
+      ga_fence_async();  // staged entries -> visible to the TMA (async proxy) reads of the next step
+    }
+    __syncthreads();  // lists of column X staged, state of X+1 ready, asynchronous copies landed
+  }
+  // last column of the chunk
+  if (is_aux && jac) {
+    write_out(X1 - 1);
+    ga_bulk_wait_read();
+  }
+}

@@ -1,0 +1,108 @@
+// cuda_emu.h -- TEST INFRASTRUCTURE ONLY: runs a CUDA kernel's source as host C++, one pthread per CUDA
+// thread, so that the index logic of gm_gath_kernel.cuh can be checked against the oracle in a container
+// without a GPU (tests/test_gath_emu.py).  Nothing under gemotion.jl_b200/ links or loads this.
+//
+// Asynchronous copies are modelled pessimistically: cp.async copies are performed when the issuing thread
+// waits for them, bulk shared->global copies read shared memory only at wait_group.read -- so data used
+// before its wait, or a staging buffer recycled too early, shows up as wrong numbers.  Shared memory is
+// poisoned with NaNs at block start.
+#pragma once
+#include <pthread.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#define GM_EMU 1
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __restrict__
+#define __align__(x)
+
+struct emu_dim3 { unsigned x = 1, y = 1, z = 1; };
+static thread_local emu_dim3 threadIdx, blockIdx;
+static emu_dim3 blockDim, gridDim;
+struct double2 { double x, y; };
+struct uint4 { uint32_t x, y, z, w; };
+using std::min;
+using std::max;
+using std::fma;
+
+#define GM_JACOBIAN 1u
+#define GM_RESIDUAL 2u
+
+static unsigned char *g_emu_smem = nullptr;
+static inline unsigned char *emu_smem() { return g_emu_smem; }
+static pthread_barrier_t g_emu_bar_all, g_emu_bar_aux;
+static inline void __syncthreads() { pthread_barrier_wait(&g_emu_bar_all); }
+static inline void ga_bar_aux() { pthread_barrier_wait(&g_emu_bar_aux); }
+
+struct EmuCopy { void *dst; const void *src; int bytes; };
+static thread_local std::vector<EmuCopy> t_emu_cp, t_emu_bulk;
+static inline void ga_cp4(void *d, const void *s) { t_emu_cp.push_back({d, s, 4}); }
+static inline void ga_cp8(void *d, const void *s) { t_emu_cp.push_back({d, s, 8}); }
+static inline void ga_cp16(void *d, const void *s) { t_emu_cp.push_back({d, s, 16}); }
+static inline void ga_cp_wait_all() {
+  for (auto &c : t_emu_cp) memcpy(c.dst, c.src, c.bytes);
+  t_emu_cp.clear();
+}
+static int64_t g_emu_bulk_misaligned = 0;
+static inline void ga_bulk_store(double *g, const double *s, int bytes) {
+  if (((uintptr_t)g & 15) || ((uintptr_t)s & 15) || (bytes & 15) || bytes <= 0) __atomic_add_fetch(&g_emu_bulk_misaligned, 1, __ATOMIC_RELAXED);
+  t_emu_bulk.push_back({g, s, bytes});
+}
+static inline void ga_bulk_commit() {}
+static inline void ga_bulk_wait_read() {
+  for (auto &c : t_emu_bulk) memcpy(c.dst, c.src, c.bytes);
+  t_emu_bulk.clear();
+}
+static inline void ga_fence_async() {}
+
+// ---- launch: blocks one after another, threads of a block concurrently
+template <typename Args>
+struct EmuLaunch {
+  void (*kernel)(Args);
+  Args args;
+  emu_dim3 bidx;
+  unsigned t;
+};
+template <typename Args>
+static void *emu_thread_main(void *p) {
+  EmuLaunch<Args> *l = (EmuLaunch<Args> *)p;
+  threadIdx.x = l->t; threadIdx.y = 0; threadIdx.z = 0;
+  blockIdx = l->bidx;
+  t_emu_cp.clear(); t_emu_bulk.clear();
+  l->kernel(l->args);
+  return nullptr;
+}
+template <typename Args>
+static int emu_launch(void (*kernel)(Args), Args args, unsigned gx, unsigned gy, unsigned nthreads, unsigned naux, size_t smem_bytes) {
+  gridDim.x = gx; gridDim.y = gy; blockDim.x = nthreads;
+  std::vector<unsigned char> smem(smem_bytes + 64);
+  g_emu_smem = (unsigned char *)(((uintptr_t)smem.data() + 63) & ~(uintptr_t)63);
+  std::vector<pthread_t> th(nthreads);
+  std::vector<EmuLaunch<Args>> la(nthreads);
+  pthread_attr_t attr;
+  pthread_attr_init(&attr);
+  pthread_attr_setstacksize(&attr, 1 << 20);
+  for (unsigned by = 0; by < gy; ++by)
+    for (unsigned bx = 0; bx < gx; ++bx) {
+      memset(g_emu_smem, 0xFF, smem_bytes);  // NaN poison
+      pthread_barrier_init(&g_emu_bar_all, nullptr, nthreads);
+      pthread_barrier_init(&g_emu_bar_aux, nullptr, naux);
+      for (unsigned t = 0; t < nthreads; ++t) {
+        la[t].kernel = kernel; la[t].args = args; la[t].bidx.x = bx; la[t].bidx.y = by; la[t].t = t;
+        if (pthread_create(&th[t], &attr, emu_thread_main<Args>, &la[t])) return -1;
+      }
+      for (unsigned t = 0; t < nthreads; ++t) pthread_join(th[t], nullptr);
+      pthread_barrier_destroy(&g_emu_bar_all);
+      pthread_barrier_destroy(&g_emu_bar_aux);
+    }
+  pthread_attr_destroy(&attr);
+  return 0;
+}
