@@ -180,7 +180,7 @@ __global__ void __launch_bounds__((3 * NG + GA_NAUX) * 32, 1) k_gath(CartArgs a)
 
   auto row_in_table = [&](int rr) { const int cy = Yc0 + rr; return rr >= 0 && rr <= nqr && cy >= 0 && cy < a.ny; };
   auto row_owned = [&](int rr) { const int cy = Yc0 + rr; return rr >= 0 && rr <= nqr && cy >= a.row_begin && cy < a.row_end; };
-  auto col_ok = [&](int c) { return c >= 0 && c < a.nx; };
+  auto col_ok = [&](int c) { return c >= 0 && c >= X0 - 1 && c < a.nx; };  // cell columns this chunk works with
 
   // ---- constant tables
   for (int k = tid; k < 36; k += NT) { s.tphi[0][k] = cc.sphi[0][k]; s.tdx[0][k] = cc.sdx[0][k]; s.tdy[0][k] = cc.sdy[0][k]; }
@@ -357,37 +357,40 @@ __global__ void __launch_bounds__((3 * NG + GA_NAUX) * 32, 1) k_gath(CartArgs a)
       }
     }
   };
-  // (A5) constant P-block entries of quad column X -> staged lists
+  // (A5) constant P-block entries of quad column X -> staged lists.  Aux thread e < 108 owns entry type e
+  //      (everything but the rank class and the list parity is loop invariant) and walks the quad rows.
+  int pe_li = 0, pe_rk = 0, pe_dx = 0, pe_dy = 0;
+  double pe_val = 0.0;
+  const bool pe_on = is_aux && at < 108, pe_plist = at >= 54;
+  if (pe_on) {
+    if (at < 54) {      // P rows (CSC) / P columns (CSR) inside the U lists of node A
+      const int An = s.pu[at][0], m = s.pu[at][1], c2 = s.pu[at][2], p = s.pu[at][3];
+      const int nd = ga_anode(An, m);
+      pe_dx = m & 1; pe_dy = m >> 1;
+      pe_li = An * 3 + c2;
+      pe_rk = (18 + p) * 30 + c2 * 9 + nd;
+      pe_val = (CSR ? 1.0 : -1.0) * s.UP[c2 * 9 + nd][p];
+    } else {            // the three P lists of the cell of this quad
+      const int p = (at - 54) / 18, ud = (at - 54) - p * 18;
+      pe_li = 12 + p;
+      pe_rk = ud * 30 + 18 + p;
+      pe_val = (CSR ? -1.0 : 1.0) * s.UP[ud][p];
+    }
+  }
   auto p_entries = [&](int X) {
-    double *stg0 = s.stage[X & 1];
-    for (int k = at; k < QH * 108; k += NAT) {
-      const int rowq = k / 108, e = k - rowq * 108;
-      if (rowq >= nqr) break;
-      int li, rkidx, upi, upp;
-      bool owned;
-      int cx, rr;
-      double sgn;
-      if (e < 54) {      // P rows (CSC) / P columns (CSR) inside the U lists of node A
-        const int An = s.pu[e][0], m = s.pu[e][1], c2 = s.pu[e][2], p = s.pu[e][3];
-        cx = X - (m & 1); rr = rowq + 1 - (m >> 1);
-        const int nd = ga_anode(An, m);
-        li = An * 3 + c2; upi = c2 * 9 + nd; upp = p;
-        rkidx = (18 + p) * 30 + upi;
-        sgn = CSR ? 1.0 : -1.0;
-      } else {           // the three P lists of the cell of this quad
-        const int p = (e - 54) / 18, ud = (e - 54) - p * 18;
-        cx = X; rr = rowq + 1;
-        li = 12 + p; upi = ud; upp = p;
-        rkidx = ud * 30 + 18 + p;
-        sgn = CSR ? -1.0 : 1.0;
-      }
-      if (!col_ok(cx) || !row_in_table(rr)) continue;
-      owned = row_owned(rr);
-      if (e >= 54 && !owned) continue;
-      const int rk = GA_LDG(a.ctab + (int64_t)s.cls[cx & 3][rr] * 900 + rkidx);
+    if (!pe_on) return;
+    const int cx = X - pe_dx;
+    if (!col_ok(cx)) return;
+    double *stg0 = s.stage[X & 1] + s.slot[pe_li];
+    for (int rowq = 0; rowq < nqr; ++rowq) {
+      const int rr = rowq + 1 - pe_dy;
+      if (!row_in_table(rr)) continue;
+      const bool owned = row_owned(rr);
+      if (pe_plist && !owned) continue;
+      const int rk = GA_LDG(a.ctab + (int64_t)s.cls[cx & 3][rr] * 900 + pe_rk);
       if (rk == 0xFF) continue;
-      const int par = (int)(s.lbase[X & 3][rowq][li] & 1);
-      stg0[rowq * GA_QSTRIDE + s.slot[li] + par + rk] = owned ? sgn * s.UP[upi][upp] : 0.0;
+      const int par = (int)(s.lbase[X & 3][rowq][pe_li] & 1);
+      stg0[rowq * GA_QSTRIDE + par + rk] = owned ? pe_val : 0.0;
     }
   };
   // (A6) residual of the dofs of quad column X: partial sums per (node, cell), then one store per dof

@@ -5,7 +5,7 @@
 // Asynchronous copies are modelled pessimistically: cp.async copies are performed when the issuing thread
 // waits for them, bulk shared->global copies read shared memory only at wait_group.read -- so data used
 // before its wait, or a staging buffer recycled too early, shows up as wrong numbers.  Shared memory is
-// poisoned with NaNs at block start.
+// poisoned at block start.
 #pragma once
 #include <pthread.h>
 #include <stdint.h>
@@ -92,7 +92,7 @@ static int emu_launch(void (*kernel)(Args), Args args, unsigned gx, unsigned gy,
   pthread_attr_setstacksize(&attr, 1 << 20);
   for (unsigned by = 0; by < gy; ++by)
     for (unsigned bx = 0; bx < gx; ++bx) {
-      memset(g_emu_smem, 0xFF, smem_bytes);  // NaN poison
+      memset(g_emu_smem, 0x7F, smem_bytes);  // poison: huge doubles, huge positive ints (a stale dof id faults)
       pthread_barrier_init(&g_emu_bar_all, nullptr, nthreads);
       pthread_barrier_init(&g_emu_bar_aux, nullptr, naux);
       for (unsigned t = 0; t < nthreads; ++t) {
