@@ -31,7 +31,8 @@
 #pragma once
 
 #define GA_XCH 128                 // quad columns per x-chunk
-#define GA_NAUX 4                  // aux warps
+#define GA_NAUX 6                  // aux warps
+#define GA_MAXREG 168               // 65536 / ((3*2 + GA_NAUX) * 32), rounded down to the allocation unit
 #define GA_QS 12                   // doubles per (variant, point) state record
 #define GA_VS 56                   // doubles per variant: 4 records + 8 (p, T of the 4 points; variant 0 only)
 #define GA_CS (4 * GA_VS + 2)      // doubles per cell (226: consecutive cell rows are shifted by 16 B in the banks)
@@ -49,6 +50,7 @@
 #define GS_SC 8
 #define GS_U0 9
 #define GS_U1 10
+#define GS_MUR 11  // plain mu (residual); GS_MU holds jac_scaling * w_q * Pr * mu
 
 #ifdef GM_EMU
 #define GA_LDG(p) (*(p))
@@ -158,7 +160,7 @@ struct GaSmem {
 };
 
 template <int NG, bool CSR, bool NEWT>
-__global__ void __launch_bounds__((3 * NG + GA_NAUX) * 32, 1) k_gath(CartArgs a) {
+__global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
   using S = GaSmem<NG>;
   constexpr int QH = S::QH, NR = S::NR;
   constexpr int NMW = 3 * NG, NMT = NMW * 32, NAT = GA_NAUX * 32, NT = NMT + NAT;
@@ -223,13 +225,15 @@ __global__ void __launch_bounds__((3 * NG + GA_NAUX) * 32, 1) k_gath(CartArgs a)
   // reference-element products of the canonical pair (test node it, trial node jt)
   const int nA = ga_node(ga_ax(A), ga_ay(A)), nB = ga_node(role.bx, role.by);
   const int it = CSR ? nA : nB, jt = CSR ? nB : nA;
-  double TA[4], TB[4], TC[4], TD[4], TM[4], TP[4], TK, TUT0, TUT1;
+  // (24 + 3 doubles in registers; the viscous products w Pr d_k phi_i d_l phi_j are formed on the fly from the
+  //  gradients, with w Pr jac_scaling folded into the state's mu: 6 extra DFMA per point instead of 32 registers)
+  double TM[4], TP[4], TK, TUT0, TUT1;
   double dix[4], diy[4], djx[4], djy[4];
   {
     const CartPairTab &t = a.tab[it * 9 + jt];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      TA[q] = t.TA[q]; TB[q] = t.TB[q]; TC[q] = t.TC[q]; TD[q] = t.TD[q]; TM[q] = t.TM[q]; TP[q] = t.TP[q];
+      TM[q] = t.TM[q]; TP[q] = t.TP[q];
       dix[q] = cc.sdx[q][it]; diy[q] = cc.sdy[q][it]; djx[q] = cc.sdx[q][jt]; djy[q] = cc.sdy[q][jt];
     }
     TK = t.TK; TUT0 = t.TUT0; TUT1 = t.TUT1;
@@ -273,9 +277,9 @@ __global__ void __launch_bounds__((3 * NG + GA_NAUX) * 32, 1) k_gath(CartArgs a)
   auto state = [&](int c) {
     if (!col_ok(c)) return;
     double *sc0 = s.st[c % 3];
-    for (int k = at; k < NR * 12; k += NAT) {
-      const int rr = k / 12, e = k - rr * 12, q = e & 3, g = e >> 2;
-      if (!row_owned(rr)) continue;
+    for (int k = at; k < 3 * 64; k += NAT) {  // g-major item order: a warp runs one kind of item
+      const int g = k >> 6, e = k & 63, rr = e >> 2, q = e & 3;
+      if (rr >= NR || !row_owned(rr)) continue;
       double *cs = sc0 + rr * GA_CS;
       const double *vv = &s.val[c & 3][rr][0];
       if (g == 0) {         // velocity
@@ -316,7 +320,7 @@ __global__ void __launch_bounds__((3 * NG + GA_NAUX) * 32, 1) k_gath(CartArgs a)
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
           double *o = cs + m * GA_VS + (q ^ m) * GA_QS;
-          o[GS_MU] = mu; o[GS_SC] = sc;
+          o[GS_MU] = a.js * s.tw[q] * a.Pr * mu; o[GS_SC] = sc; o[GS_MUR] = mu;
         }
         cs[4 * GA_QS + 2 * q] = p;
       }
@@ -410,7 +414,7 @@ __global__ void __launch_bounds__((3 * NG + GA_NAUX) * 32, 1) k_gath(CartArgs a)
             const double ph = w * s.tphi[q][nd], dx = w * gx_, dy = w * gy_;
             const double u0 = u[GS_U0], u1 = u[GS_U1], G00 = u[GS_G00], G01 = u[GS_G01], G10 = u[GS_G10], G11 = u[GS_G11];
             const double D01 = u[GS_D01], pq = cs[4 * GA_QS + 2 * q], Tq = cs[4 * GA_QS + 2 * q + 1];
-            const double m2 = 2.0 * a.Pr * w * u[GS_MU], bu = a.RaPr * Tq;
+            const double m2 = 2.0 * a.Pr * w * u[GS_MUR], bu = a.RaPr * Tq;
             r0 = fma(m2, fma(G00, gx_, D01 * gy_), r0); r0 = fma(ph, fma(u0, G00, u1 * G10) - bu * a.gx, r0); r0 = fma(-dx, pq, r0);
             r1 = fma(m2, fma(D01, gx_, G11 * gy_), r1); r1 = fma(ph, fma(u0, G01, u1 * G11) - bu * a.gy, r1); r1 = fma(-dy, pq, r1);
             r2 = fma(u[GS_DT0], dx, r2); r2 = fma(u[GS_DT1], dy, r2); r2 = fma(fma(u0, u[GS_DT0], u1 * u[GS_DT1]), ph, r2);
@@ -484,6 +488,20 @@ __global__ void __launch_bounds__((3 * NG + GA_NAUX) * 32, 1) k_gath(CartArgs a)
       double v00 = 0, v01 = 0, v10 = 0, v11 = 0, tu0 = 0, tu1 = 0, tt = 0, ut0 = 0, ut1 = 0;
       uint32_t rk0 = 0, rk1 = 0, rk2 = 0;
       bool have = false;
+      // rank records of the four rounds and list parities of the flushing rounds: all loads up front
+      uint4 rec[4];
+      uint32_t parm = 0;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const uint32_t info = R[r];
+        const int cx = X - (int)((info >> 4) & 1);
+        if (cx >= 0 && cx < a.nx && (info & (1u << 18)))
+          rec[r] = GA_LDG(reinterpret_cast<const uint4 *>(a.ptab) + ((int64_t)s.cls[cx & 3][info & 15] * 81 + ((info >> 11) & 127)));
+        if (info & (1u << 6)) {
+          const int *lb = reinterpret_cast<const int *>(&s.lbase[X & 3][(info >> 7) & 15][A * 3]);
+          parm |= (uint32_t)((lb[0] & 1) | ((lb[2] & 1) << 1) | ((lb[4] & 1) << 2)) << (3 * r);
+        }
+      }
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const uint32_t info = R[r];
@@ -491,8 +509,7 @@ __global__ void __launch_bounds__((3 * NG + GA_NAUX) * 32, 1) k_gath(CartArgs a)
         const int cx = X - mx;
         const bool cok = cx >= 0 && cx < a.nx;
         if (cok && (info & (1u << 18))) {
-          const uint4 rec = GA_LDG(reinterpret_cast<const uint4 *>(a.ptab) + ((int64_t)s.cls[cx & 3][rr] * 81 + ((info >> 11) & 127)));
-          rk0 = rec.x; rk1 = rec.y; rk2 = rec.z;
+          rk0 = rec[r].x; rk1 = rec[r].y; rk2 = rec[r].z;
           have = true;
         }
         if (cok && (info & (1u << 19))) {
@@ -503,8 +520,12 @@ __global__ void __launch_bounds__((3 * NG + GA_NAUX) * 32, 1) k_gath(CartArgs a)
           for (int q = 0; q < 4; ++q) {
             const double2 a0 = sp[q * 6 + 0], a1 = sp[q * 6 + 1], a2 = sp[q * 6 + 2], a3 = sp[q * 6 + 3], a4 = sp[q * 6 + 4],
                           a5 = sp[q * 6 + 5];  // (mu,G00) (G01,G10) (G11,D01) (dT0,dT1) (sc,u0) (u1,-)
-            const double mu = a0.x;
-            w00 = fma(mu, TA[q], w00); w11 = fma(mu, TB[q], w11); w01 = fma(mu, TC[q], w01); w10 = fma(mu, TD[q], w10);
+            {  // viscous: mu' (2 d_x d_x + d_y d_y, d_y phi_i d_x phi_j; d_x phi_i d_y phi_j, d_x d_x + 2 d_y d_y), mu' = jac_scaling w Pr mu
+              const double mu = a0.x;
+              const double pxx = dix[q] * djx[q], pyy = diy[q] * djy[q], pyx = diy[q] * djx[q], pxy = dix[q] * djy[q];
+              w00 = fma(mu, fma(2.0, pxx, pyy), w00); w11 = fma(mu, fma(2.0, pyy, pxx), w11);
+              w01 = fma(mu, pyx, w01); w10 = fma(mu, pxy, w10);
+            }
             if (!NEWT) {
               // S_ia = sum_k D[k][a] d_k phi_i (test), S'_jb = sc * S_jb (trial)   
               const double D01 = a2.y;
@@ -529,8 +550,8 @@ __global__ void __launch_bounds__((3 * NG + GA_NAUX) * 32, 1) k_gath(CartArgs a)
           if (have) {
             const int rowq = (info >> 7) & 15;
             double *q0 = stg0 + rowq * GA_QSTRIDE;
-            const int *lb = reinterpret_cast<const int *>(&s.lbase[X & 3][rowq][A * 3]);
-            double *b0 = q0 + slotA0 + (lb[0] & 1), *b1 = q0 + slotA1 + (lb[2] & 1), *b2 = q0 + slotA2 + (lb[4] & 1);
+            const uint32_t pm = parm >> (3 * r);
+            double *b0 = q0 + slotA0 + (pm & 1), *b1 = q0 + slotA1 + ((pm >> 1) & 1), *b2 = q0 + slotA2 + ((pm >> 2) & 1);
             double e00, e01, e02, e10, e11, e12, e20, e21, e22;  // [list k][minor dof l]
             if (CSR) { e00 = v00; e01 = v01; e02 = ut0; e10 = v10; e11 = v11; e12 = ut1; e20 = tu0; e21 = tu1; e22 = tt; }
             else     { e00 = v00; e01 = v10; e02 = tu0; e10 = v01; e11 = v11; e12 = tu1; e20 = ut0; e21 = ut1; e22 = tt; }

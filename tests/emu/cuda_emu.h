@@ -21,6 +21,7 @@
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
+#define __maxnreg__(...)
 #define __restrict__
 #define __align__(x)
 
