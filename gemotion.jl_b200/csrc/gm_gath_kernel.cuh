@@ -31,8 +31,8 @@
 #pragma once
 
 #define GA_XCH 128                 // quad columns per x-chunk
-#define GA_NAUX 6                  // aux warps
-#define GA_MAXREG 168               // 65536 / ((3*2 + GA_NAUX) * 32), rounded down to the allocation unit
+#define GA_NAUX 5                  // aux warps
+#define GA_MAXREG 184               // 65536 / ((3*2 + GA_NAUX) * 32), rounded down to the allocation unit
 #define GA_QS 12                   // doubles per (variant, point) state record
 #define GA_VS 56                   // doubles per variant: 4 records + 8 (p, T of the 4 points; variant 0 only)
 #define GA_CS (4 * GA_VS + 2)      // doubles per cell (226: consecutive cell rows are shifted by 16 B in the banks)
@@ -84,7 +84,9 @@ __device__ __forceinline__ void ga_bulk_store(double *gdst, const double *ssrc, 
 __device__ __forceinline__ void ga_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void ga_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void ga_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void ga_bar_aux() { asm volatile("bar.sync 2, %0;" ::"n"(GA_NAUX * 32) : "memory"); }
+__device__ __forceinline__ double ga_shfl_xor(double v, int mask) { return __shfl_xor_sync(0xffffffffu, v, mask); }
+template <int NT>
+__device__ __forceinline__ void ga_bar_step() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }  // both role loops meet here
 #endif
 
 // local node index of the tensor position (ix, iy) of a Q2 cell (same table as c_ct_node)
@@ -149,7 +151,6 @@ struct GaSmem {
   double visc[4][NR][4][2];
   long long lbase[4][QH][16];        // list bases / ends of quad column X (X & 3); 15 used
   long long lnext[4][QH][16];
-  double respart[QH][16][3];         // residual partial sums [quad row][A*4 + cell][k]
   double tphi[4][9], tdx[4][9], tdy[4][9], tw[4], twpsi[4][3], tpsi[4][3];
   double UP[18][3];
   int32_t gd[8][NR][30];             // dof ids of cell column c (c & 7)
@@ -180,8 +181,11 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
   const bool jac = (a.flags & GM_JACOBIAN) != 0, res = (a.flags & GM_RESIDUAL) != 0;
   const CartCell &cc = *a.cc;
 
-  auto row_in_table = [&](int rr) { const int cy = Yc0 + rr; return rr >= 0 && rr <= nqr && cy >= 0 && cy < a.ny; };
-  auto row_owned = [&](int rr) { const int cy = Yc0 + rr; return rr >= 0 && rr <= nqr && cy >= a.row_begin && cy < a.row_end; };
+  // state rows (cell rows Yc0 + rr, rr = 0..nqr) that exist in the local table / are owned by this rank
+  const int tab_lo = max(0, -Yc0), tab_n = min(nqr, a.ny - 1 - Yc0) - tab_lo;
+  const int own_lo = max(0, a.row_begin - Yc0), own_n = min(nqr, a.row_end - 1 - Yc0) - own_lo;
+  auto row_in_table = [&](int rr) { return (unsigned)(rr - tab_lo) <= (unsigned)tab_n && tab_n >= 0; };
+  auto row_owned = [&](int rr) { return (unsigned)(rr - own_lo) <= (unsigned)own_n && own_n >= 0; };
   auto col_ok = [&](int c) { return c >= 0 && c >= X0 - 1 && c < a.nx; };  // cell columns this chunk works with
 
   // ---- constant tables
@@ -202,48 +206,13 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
           }
   }
 
-  // ---- role of a matrix lane
-  const int grp = is_aux ? 0 : warp / 3, wl = warp % 3;
-  const bool lane_on = !is_aux && lane < 27;
-  const GaRole role = ga_role(lane_on ? wl * 27 + lane : 0);
-  const int A = role.A;
-  uint32_t R[4];  // per round: [0:3] state row, [4:5] variant, [6] flush, [7:10] quad row, [11:17] pair index, [18] in table, [19] owned
-  {
-    const int ax = ga_ax(A), ay = ga_ay(A);
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int m = role.m[r], mx = m & 1, my = m >> 1;
-      const int rowq = grp * 4 + role.gq[r], rr = rowq + 1 - my;
-      const bool rq_ok = lane_on && rowq < nqr;
-      const int Mact = ga_node(mx ? 2 - ax : ax, my ? 2 - ay : ay);
-      const int mact = ga_node(mx ? 2 - role.bx : role.bx, my ? 2 - role.by : role.by);
-      R[r] = (uint32_t)rr | ((uint32_t)m << 4) | ((uint32_t)role.flush[r] << 6) | ((uint32_t)rowq << 7) |
-             ((uint32_t)(Mact * 9 + mact) << 11) | ((rq_ok && row_in_table(rr)) ? (1u << 18) : 0u) |
-             ((rq_ok && row_owned(rr)) ? (1u << 19) : 0u);
-    }
-  }
-  // reference-element products of the canonical pair (test node it, trial node jt)
-  const int nA = ga_node(ga_ax(A), ga_ay(A)), nB = ga_node(role.bx, role.by);
-  const int it = CSR ? nA : nB, jt = CSR ? nB : nA;
-  // (24 + 3 doubles in registers; the viscous products w Pr d_k phi_i d_l phi_j are formed on the fly from the
-  //  gradients, with w Pr jac_scaling folded into the state's mu: 6 extra DFMA per point instead of 32 registers)
-  double TM[4], TP[4], TK, TUT0, TUT1;
-  double dix[4], diy[4], djx[4], djy[4];
-  {
-    const CartPairTab &t = a.tab[it * 9 + jt];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      TM[q] = t.TM[q]; TP[q] = t.TP[q];
-      dix[q] = cc.sdx[q][it]; diy[q] = cc.sdy[q][it]; djx[q] = cc.sdx[q][jt]; djy[q] = cc.sdy[q][jt];
-    }
-    TK = t.TK; TUT0 = t.TUT0; TUT1 = t.TUT1;
-  }
-  const int slotA0 = A == 0 ? 0 : (A == 1 ? 252 : (A == 2 ? 402 : 552));
-  const int slotA1 = slotA0 + (A == 0 ? 88 : (A == 3 ? 32 : 52));
-  const int slotA2 = slotA1 + (A == 0 ? 88 : (A == 3 ? 32 : 52));
-
   __syncthreads();
 
+  // =====================================================================================
+  // column sweep (two role-specific loops, so that the registers of one role are not live in the other).  Step X (matrix: quad column X): aux prepares dof ids of X+3, values of X+2, state and
+  // list records of X+1.  Four warm-up steps fill the pipeline.
+  // =====================================================================================
+  if (is_aux) {
   // =====================================================================================
   // aux tasks
   // =====================================================================================
@@ -386,20 +355,27 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
     const int cx = X - pe_dx;
     if (!col_ok(cx)) return;
     double *stg0 = s.stage[X & 1] + s.slot[pe_li];
-    for (int rowq = 0; rowq < nqr; ++rowq) {
+    int rk[QH];
+    bool own[QH];
+#pragma unroll
+    for (int rowq = 0; rowq < QH; ++rowq) {  // all rank loads in flight together
       const int rr = rowq + 1 - pe_dy;
-      if (!row_in_table(rr)) continue;
-      const bool owned = row_owned(rr);
-      if (pe_plist && !owned) continue;
-      const int rk = GA_LDG(a.ctab + (int64_t)s.cls[cx & 3][rr] * 900 + pe_rk);
-      if (rk == 0xFF) continue;
+      own[rowq] = row_owned(rr);
+      const bool ok = rowq < nqr && row_in_table(rr) && (own[rowq] || !pe_plist);
+      rk[rowq] = ok ? (int)GA_LDG(a.ctab + (int64_t)s.cls[cx & 3][ok ? rr : 0] * 900 + pe_rk) : 0xFF;
+    }
+#pragma unroll
+    for (int rowq = 0; rowq < QH; ++rowq) {
+      if (rk[rowq] == 0xFF) continue;
       const int par = (int)(s.lbase[X & 3][rowq][pe_li] & 1);
-      stg0[rowq * GA_QSTRIDE + par + rk] = owned ? pe_val : 0.0;
+      stg0[rowq * GA_QSTRIDE + par + rk[rowq]] = own[rowq] ? pe_val : 0.0;
     }
   };
-  // (A6) residual of the dofs of quad column X: partial sums per (node, cell), then one store per dof
+  // (A6) residual of the dofs of quad column X: lane quartet = the (up to) four cells of one node; partial sums
+  //      are combined by two butterfly shuffles, lane 0 of the quartet stores the three dofs of the node
   auto residual = [&](int X) {
-    for (int k = at; k < QH * 16; k += NAT) {
+    for (int k0 = 0; k0 < QH * 16; k0 += NAT) {  // (NAT is a multiple of 32: whole warps enter together)
+      const int k = k0 + at;
       const int rowq = k >> 4, An = (k >> 2) & 3, sv = k & 3;
       double r0 = 0, r1 = 0, r2 = 0;
       if (rowq < nqr && sv < ga_nvar(An)) {
@@ -421,28 +397,26 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
           }
         }
       }
-      s.respart[rowq][k & 15][0] = r0; s.respart[rowq][k & 15][1] = r1; s.respart[rowq][k & 15][2] = r2;
-    }
-    ga_bar_aux();
-    for (int k = at; k < QH * 15; k += NAT) {
-      const int rowq = k / 15, li = k - rowq * 15;
-      if (rowq >= nqr) break;
-      const int32_t g = s.lg[X & 3][rowq][li];
-      if (g <= 0) continue;
-      double v;
-      if (li < 12) {
-        const int An = li / 3, kk = li - An * 3;
-        v = (s.respart[rowq][An * 4][kk] + s.respart[rowq][An * 4 + 1][kk]) + (s.respart[rowq][An * 4 + 2][kk] + s.respart[rowq][An * 4 + 3][kk]);
-      } else {
-        const int p = li - 12;
-        const double *cs = s.st[X % 3] + (rowq + 1) * GA_CS;
-        v = 0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) v += s.twpsi[q][p] * (cs[q * GA_QS + GS_G00] + cs[q * GA_QS + GS_G11]);
+      r0 += ga_shfl_xor(r0, 1); r1 += ga_shfl_xor(r1, 1); r2 += ga_shfl_xor(r2, 1);
+      r0 += ga_shfl_xor(r0, 2); r1 += ga_shfl_xor(r1, 2); r2 += ga_shfl_xor(r2, 2);
+      if (sv == 0 && rowq < nqr) {
+        const int32_t *lg = &s.lg[X & 3][rowq][An * 3];
+        if (lg[0] > 0) a.b[lg[0] - 1] = r0;
+        if (lg[1] > 0) a.b[lg[1] - 1] = r1;
+        if (lg[2] > 0) a.b[lg[2] - 1] = r2;
       }
+    }
+    for (int k = at; k < QH * 3; k += NAT) {  // pressure rows: cell-local
+      const int rowq = k / 3, p = k - rowq * 3;
+      if (rowq >= nqr) break;
+      const int32_t g = s.lg[X & 3][rowq][12 + p];
+      if (g <= 0) continue;
+      const double *cs = s.st[X % 3] + (rowq + 1) * GA_CS;
+      double v = 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v += s.twpsi[q][p] * (cs[q * GA_QS + GS_G00] + cs[q * GA_QS + GS_G11]);
       a.b[g - 1] = v;
     }
-    ga_bar_aux();  // respart is reused by the next column
   };
   // (A7) write-out of quad column X: one TMA bulk copy per completed list
   auto write_out = [&](int X) {
@@ -465,13 +439,8 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
     ga_bulk_commit();
   };
 
-  // =====================================================================================
-  // column sweep.  Step X (matrix: quad column X): aux prepares dof ids of X+3, values of X+2, state and
-  // list records of X+1.  Four warm-up steps fill the pipeline.
-  // =====================================================================================
-  for (int X = X0 - 4; X < X1; ++X) {
-    const bool live = X >= X0;
-    if (is_aux) {
+    for (int X = X0 - 4; X < X1; ++X) {
+      const bool live = X >= X0;
       if (live && X > X0 && jac) write_out(X - 1);
       issue_gd(X + 3);
       issue_val(X + 2);
@@ -482,8 +451,57 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
       ga_cp_wait_all();
       ga_bulk_wait_read();
       ga_fence_async();
-    } else if (live && jac) {
-      const double *stc0 = s.st[X % 3], *stc1 = s.st[(X + 2) % 3];  // cell columns X and X-1
+      ga_bar_step<NT>();  // lists of column X staged, state of X+1 ready, asynchronous copies landed
+    }
+    if (jac) {  // last column of the chunk
+      write_out(X1 - 1);
+      ga_bulk_wait_read();
+    }
+  } else {
+  // ---- role of a matrix lane
+  const int grp = is_aux ? 0 : warp / 3, wl = warp % 3;
+  const bool lane_on = !is_aux && lane < 27;
+  const GaRole role = ga_role(lane_on ? wl * 27 + lane : 0);
+  const int A = role.A;
+  uint32_t R[4];  // per round: [0:3] state row, [4:5] variant, [6] flush, [7:10] quad row, [11:17] pair index, [18] in table, [19] owned
+  {
+    const int ax = ga_ax(A), ay = ga_ay(A);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int m = role.m[r], mx = m & 1, my = m >> 1;
+      const int rowq = grp * 4 + role.gq[r], rr = rowq + 1 - my;
+      const bool rq_ok = lane_on && rowq < nqr;
+      const int Mact = ga_node(mx ? 2 - ax : ax, my ? 2 - ay : ay);
+      const int mact = ga_node(mx ? 2 - role.bx : role.bx, my ? 2 - role.by : role.by);
+      R[r] = (uint32_t)rr | ((uint32_t)m << 4) | ((uint32_t)role.flush[r] << 6) | ((uint32_t)rowq << 7) |
+             ((uint32_t)(Mact * 9 + mact) << 11) | ((rq_ok && row_in_table(rr)) ? (1u << 18) : 0u) |
+             ((rq_ok && row_owned(rr)) ? (1u << 19) : 0u);
+    }
+  }
+  // reference-element products of the canonical pair (test node it, trial node jt)
+  const int nA = ga_node(ga_ax(A), ga_ay(A)), nB = ga_node(role.bx, role.by);
+  const int it = CSR ? nA : nB, jt = CSR ? nB : nA;
+  // (24 + 3 doubles in registers; the viscous products w Pr d_k phi_i d_l phi_j are formed on the fly from the
+  //  gradients, with w Pr jac_scaling folded into the state's mu: 6 extra DFMA per point instead of 32 registers)
+  double TM[4], TP[4], TK, TUT0, TUT1;
+  double dix[4], diy[4], djx[4], djy[4];
+  {
+    const CartPairTab &t = a.tab[it * 9 + jt];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      TM[q] = t.TM[q]; TP[q] = t.TP[q];
+      dix[q] = cc.sdx[q][it]; diy[q] = cc.sdy[q][it]; djx[q] = cc.sdx[q][jt]; djy[q] = cc.sdy[q][jt];
+    }
+    TK = t.TK; TUT0 = t.TUT0; TUT1 = t.TUT1;
+  }
+  const int slotA0 = A == 0 ? 0 : (A == 1 ? 252 : (A == 2 ? 402 : 552));
+  const int slotA1 = slotA0 + (A == 0 ? 88 : (A == 3 ? 32 : 52));
+  const int slotA2 = slotA1 + (A == 0 ? 88 : (A == 3 ? 32 : 52));
+
+    int xm3 = X0 % 3;
+    for (int X = X0 - 4; X < X1; ++X) {
+      if (X >= X0 && jac) {
+      const double *stc0 = s.st[xm3], *stc1 = s.st[xm3 == 0 ? 2 : xm3 - 1];  // cell columns X and X-1
       double *stg0 = s.stage[X & 1];
       double v00 = 0, v01 = 0, v10 = 0, v11 = 0, tu0 = 0, tu1 = 0, tt = 0, ut0 = 0, ut1 = 0;
       uint32_t rk0 = 0, rk1 = 0, rk2 = 0;
@@ -571,12 +589,9 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
         }
       }
       ga_fence_async();  // staged entries -> visible to the TMA (async proxy) reads of the next step
+        xm3 = xm3 == 2 ? 0 : xm3 + 1;
+      }
+      ga_bar_step<NT>();
     }
-    __syncthreads();  // lists of column X staged, state of X+1 ready, asynchronous copies landed
-  }
-  // last column of the chunk
-  if (is_aux && jac) {
-    write_out(X1 - 1);
-    ga_bulk_wait_read();
   }
 }

@@ -39,9 +39,20 @@ using std::fma;
 
 static unsigned char *g_emu_smem = nullptr;
 static inline unsigned char *emu_smem() { return g_emu_smem; }
-static pthread_barrier_t g_emu_bar_all, g_emu_bar_aux;
+static pthread_barrier_t g_emu_bar_all, g_emu_bar_warp[64];
+static double g_emu_xbuf[64][32];
 static inline void __syncthreads() { pthread_barrier_wait(&g_emu_bar_all); }
-static inline void ga_bar_aux() { pthread_barrier_wait(&g_emu_bar_aux); }
+template <int NT>
+static inline void ga_bar_step() { pthread_barrier_wait(&g_emu_bar_all); }
+// full-warp butterfly shuffle: all 32 threads of the warp must call it
+static inline double ga_shfl_xor(double v, int mask) {
+  const unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  g_emu_xbuf[w][l] = v;
+  pthread_barrier_wait(&g_emu_bar_warp[w]);
+  const double r = g_emu_xbuf[w][l ^ mask];
+  pthread_barrier_wait(&g_emu_bar_warp[w]);
+  return r;
+}
 
 struct EmuCopy { void *dst; const void *src; int bytes; };
 static thread_local std::vector<EmuCopy> t_emu_cp, t_emu_bulk;
@@ -95,14 +106,14 @@ static int emu_launch(void (*kernel)(Args), Args args, unsigned gx, unsigned gy,
     for (unsigned bx = 0; bx < gx; ++bx) {
       memset(g_emu_smem, 0x7F, smem_bytes);  // poison: huge doubles, huge positive ints (a stale dof id faults)
       pthread_barrier_init(&g_emu_bar_all, nullptr, nthreads);
-      pthread_barrier_init(&g_emu_bar_aux, nullptr, naux);
+      for (unsigned w = 0; w < nthreads / 32; ++w) pthread_barrier_init(&g_emu_bar_warp[w], nullptr, 32);
       for (unsigned t = 0; t < nthreads; ++t) {
         la[t].kernel = kernel; la[t].args = args; la[t].bidx.x = bx; la[t].bidx.y = by; la[t].t = t;
         if (pthread_create(&th[t], &attr, emu_thread_main<Args>, &la[t])) return -1;
       }
       for (unsigned t = 0; t < nthreads; ++t) pthread_join(th[t], nullptr);
       pthread_barrier_destroy(&g_emu_bar_all);
-      pthread_barrier_destroy(&g_emu_bar_aux);
+      for (unsigned w = 0; w < nthreads / 32; ++w) pthread_barrier_destroy(&g_emu_bar_warp[w]);
     }
   pthread_attr_destroy(&attr);
   return 0;
