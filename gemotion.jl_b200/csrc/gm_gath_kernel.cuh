@@ -31,8 +31,8 @@
 #pragma once
 
 #define GA_XCH 128                 // quad columns per x-chunk
-#define GA_NAUX 5                  // aux warps
-#define GA_MAXREG 184               // 65536 / ((3*2 + GA_NAUX) * 32), rounded down to the allocation unit
+#define GA_NAUX 6                  // aux warps
+#define GA_MAXREG 168               // 65536 / (12 warps * 32): warps are allocated in fours
 #define GA_QS 12                   // doubles per (variant, point) state record
 #define GA_VS 56                   // doubles per variant: 4 records + 8 (p, T of the 4 points; variant 0 only)
 #define GA_CS (4 * GA_VS + 2)      // doubles per cell (226: consecutive cell rows are shifted by 16 B in the banks)
@@ -483,7 +483,7 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
   const int it = CSR ? nA : nB, jt = CSR ? nB : nA;
   // (24 + 3 doubles in registers; the viscous products w Pr d_k phi_i d_l phi_j are formed on the fly from the
   //  gradients, with w Pr jac_scaling folded into the state's mu: 6 extra DFMA per point instead of 32 registers)
-  double TM[4], TP[4], TK, TUT0, TUT1;
+  double TM[4], TP[4], TK;
   double dix[4], diy[4], djx[4], djy[4];
   {
     const CartPairTab &t = a.tab[it * 9 + jt];
@@ -492,18 +492,16 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
       TM[q] = t.TM[q]; TP[q] = t.TP[q];
       dix[q] = cc.sdx[q][it]; diy[q] = cc.sdy[q][it]; djx[q] = cc.sdx[q][jt]; djy[q] = cc.sdy[q][jt];
     }
-    TK = t.TK; TUT0 = t.TUT0; TUT1 = t.TUT1;
+    TK = t.TK;
   }
-  const int slotA0 = A == 0 ? 0 : (A == 1 ? 252 : (A == 2 ? 402 : 552));
-  const int slotA1 = slotA0 + (A == 0 ? 88 : (A == 3 ? 32 : 52));
-  const int slotA2 = slotA1 + (A == 0 ? 88 : (A == 3 ? 32 : 52));
 
     int xm3 = X0 % 3;
     for (int X = X0 - 4; X < X1; ++X) {
       if (X >= X0 && jac) {
       const double *stc0 = s.st[xm3], *stc1 = s.st[xm3 == 0 ? 2 : xm3 - 1];  // cell columns X and X-1
       double *stg0 = s.stage[X & 1];
-      double v00 = 0, v01 = 0, v10 = 0, v11 = 0, tu0 = 0, tu1 = 0, tt = 0, ut0 = 0, ut1 = 0;
+      double v00 = 0, v01 = 0, v10 = 0, v11 = 0, tu0 = 0, tu1 = 0, tt = 0;
+        int nev = 0;  // cells summed into the current output (constant parts are added at the flush)
       uint32_t rk0 = 0, rk1 = 0, rk2 = 0;
       bool have = false;
       // rank records of the four rounds and list parities of the flushing rounds: all loads up front
@@ -562,14 +560,20 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
           }
           v00 += w00 + e; v11 += w11 + e;
           v01 = fma(sg, w01, v01); v10 = fma(sg, w10, v10);
-          tt += TK + e; ut0 += TUT0; ut1 += TUT1;
+          tt += e;
+          ++nev;
         }
         if (info & (1u << 6)) {
           if (have) {
             const int rowq = (info >> 7) & 15;
             double *q0 = stg0 + rowq * GA_QSTRIDE;
             const uint32_t pm = parm >> (3 * r);
-            double *b0 = q0 + slotA0 + (pm & 1), *b1 = q0 + slotA1 + ((pm >> 1) & 1), *b2 = q0 + slotA2 + ((pm >> 2) & 1);
+            const int slot0 = A == 0 ? 0 : (A == 1 ? 252 : (A == 2 ? 402 : 552)), slen = A == 0 ? 88 : (A == 3 ? 32 : 52);
+            double *b0 = q0 + slot0 + (pm & 1), *b1 = q0 + slot0 + slen + ((pm >> 1) & 1), *b2 = q0 + slot0 + 2 * slen + ((pm >> 2) & 1);
+            // constant parts: nev * (TK ; buoyancy -Ra Pr g_a sum_q w phi_i phi_j)
+            const double cn = (double)nev, mb = cn * ((TM[0] + TM[1]) + (TM[2] + TM[3]));
+            const double ut0 = -a.RaPr * a.gx * mb, ut1 = -a.RaPr * a.gy * mb;
+            tt = fma(cn, TK, tt);
             double e00, e01, e02, e10, e11, e12, e20, e21, e22;  // [list k][minor dof l]
             if (CSR) { e00 = v00; e01 = v01; e02 = ut0; e10 = v10; e11 = v11; e12 = ut1; e20 = tu0; e21 = tu1; e22 = tt; }
             else     { e00 = v00; e01 = v10; e02 = tu0; e10 = v01; e11 = v11; e12 = tu1; e20 = ut0; e21 = ut1; e22 = tt; }
@@ -584,7 +588,8 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
             rk = rk1 >> 24;         if (rk != 255) b2[rk] = e21;
             rk = rk2 & 255;         if (rk != 255) b2[rk] = e22;
           }
-          v00 = v01 = v10 = v11 = tu0 = tu1 = tt = ut0 = ut1 = 0;
+          v00 = v01 = v10 = v11 = tu0 = tu1 = tt = 0;
+          nev = 0;
           have = false;
         }
       }
