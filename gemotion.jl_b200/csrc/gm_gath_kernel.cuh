@@ -33,24 +33,31 @@
 #define GA_XCH 128                 // quad columns per x-chunk
 #define GA_NAUX 6                  // aux warps
 #define GA_MAXREG 168               // 65536 / (12 warps * 32): warps are allocated in fours
-#define GA_QS 12                   // doubles per (variant, point) state record
-#define GA_VS 56                   // doubles per variant: 4 records + 8 (p, T of the 4 points; variant 0 only)
-#define GA_CS (4 * GA_VS + 2)      // doubles per cell (226: consecutive cell rows are shifted by 16 B in the banks)
+#define GA_QS 16                   // doubles per (variant, point) state record
+#define GA_VS 72                   // doubles per variant: 4 records + 8 (p, T of the 4 points; variant 0 only); 64 B bank shift
+#define GA_CS (4 * GA_VS + 2)      // doubles per cell (290: consecutive cell rows are shifted by 16 B in the banks)
 #define GA_QSTRIDE 708             // staged doubles per quad: 15 list slots (704) + bank shift
 
-// state record layout (doubles): (mu,G00) (G01,G10) (G11,D01) (dT0,dT1) (sc,u0) (u1,-)
-#define GS_MU 0
-#define GS_G00 1
-#define GS_G01 2
-#define GS_G10 3
-#define GS_G11 4
-#define GS_D01 5
-#define GS_DT0 6
-#define GS_DT1 7
-#define GS_SC 8
-#define GS_U0 9
-#define GS_U1 10
-#define GS_MUR 11  // plain mu (residual); GS_MU holds jac_scaling * w_q * Pr * mu
+// State record of one quadrature point (doubles).  The UU block of a node pair is
+//   K_ab = sum_q sum_kl C^ab_kl(q) (d_k phi_i d_l phi_j)(q) + ...   (viscous part + power-law tangent, Solver.jl:131-134)
+// and the 16 coefficients C^ab_kl = mu' V^ab_kl + sc D_ak D_bl reduce to six per point (mu' = js w Pr mu, sc = js w 2 Pr kappa):
+//   A0 = 2 mu' + sc D00^2, A1 = 2 mu' + sc D11^2, BM = mu' + sc D01^2, AA = sc D00 D11, C1 = sc D00 D01, C2 = sc D01 D11
+// so a lane needs only its four gradient products per point (registers) and no per-lane S vectors.
+#define GS_A0 0
+#define GS_A1 1
+#define GS_BM 2
+#define GS_AA 3
+#define GS_C1 4
+#define GS_C2 5
+#define GS_G00 6
+#define GS_G11 7
+#define GS_G01 8
+#define GS_G10 9
+#define GS_DT0 10
+#define GS_DT1 11
+#define GS_U0 12
+#define GS_U1 13
+#define GS_MUR 14  // plain mu (residual, variant 0)
 
 #ifdef GM_EMU
 #define GA_LDG(p) (*(p))
@@ -246,7 +253,8 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
   auto state = [&](int c) {
     if (!col_ok(c)) return;
     double *sc0 = s.st[c % 3];
-    for (int k = at; k < 3 * 64; k += NAT) {  // g-major item order: a warp runs one kind of item
+    for (int k0 = at; k0 < 3 * 64; k0 += NAT) {  // g-major item order: a warp runs one kind of item;
+      const int k = (k0 + 64) % 192;              // the velocity items go to the warps without residual work
       const int g = k >> 6, e = k & 63, rr = e >> 2, q = e & 3;
       if (rr >= NR || !row_owned(rr)) continue;
       double *cs = sc0 + rr * GA_CS;
@@ -260,13 +268,20 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
           u1 = fma(ph, uy, u1); G01 = fma(dx, uy, G01); G11 = fma(dy, uy, G11);
         }
         const double D01 = 0.5 * (G01 + G10);
+        const double mu = NEWT ? 1.0 : s.visc[c & 3][rr][q][0];
+        const double wj = a.js * s.tw[q] * a.Pr, mup = wj * mu, sc = NEWT ? 0.0 : 2.0 * wj * s.visc[c & 3][rr][q][1];
+        const double s00 = sc * G00, s01 = sc * D01, s11 = sc * G11;
+        const double A0 = fma(s00, G00, 2.0 * mup), A1 = fma(s11, G11, 2.0 * mup), BM = fma(s01, D01, mup);
+        const double AA = s00 * G11, C1 = s00 * D01, C2 = s01 * G11;
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
           const double sx = (m & 1) ? -1.0 : 1.0, sy = (m & 2) ? -1.0 : 1.0, sxy = sx * sy;
           double *o = cs + m * GA_VS + (q ^ m) * GA_QS;
-          o[GS_G00] = G00; o[GS_G01] = sxy * G01; o[GS_G10] = sxy * G10; o[GS_G11] = G11; o[GS_D01] = sxy * D01;
+          o[GS_A0] = A0; o[GS_A1] = A1; o[GS_BM] = BM; o[GS_AA] = AA; o[GS_C1] = sxy * C1; o[GS_C2] = sxy * C2;
+          o[GS_G00] = G00; o[GS_G01] = sxy * G01; o[GS_G10] = sxy * G10; o[GS_G11] = G11;
           o[GS_U0] = sx * u0; o[GS_U1] = sy * u1;
         }
+        cs[q * GA_QS + GS_MUR] = mu;
       } else if (g == 1) {  // temperature
         double T = 0, d0 = 0, d1 = 0;
 #pragma unroll
@@ -280,17 +295,10 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
           o[GS_DT0] = d0; o[GS_DT1] = d1;
         }
         cs[4 * GA_QS + 2 * q + 1] = T;
-      } else {              // pressure, viscosity
+      } else {              // pressure
         double p = 0;
 #pragma unroll
         for (int m = 0; m < 3; ++m) p += s.tpsi[q][m] * vv[18 + m];
-        const double mu = NEWT ? 1.0 : s.visc[c & 3][rr][q][0];
-        const double sc = NEWT ? 0.0 : a.js * s.tw[q] * 2.0 * a.Pr * s.visc[c & 3][rr][q][1];
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          double *o = cs + m * GA_VS + (q ^ m) * GA_QS;
-          o[GS_MU] = a.js * s.tw[q] * a.Pr * mu; o[GS_SC] = sc; o[GS_MUR] = mu;
-        }
         cs[4 * GA_QS + 2 * q] = p;
       }
     }
@@ -334,17 +342,18 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
   //      (everything but the rank class and the list parity is loop invariant) and walks the quad rows.
   int pe_li = 0, pe_rk = 0, pe_dx = 0, pe_dy = 0;
   double pe_val = 0.0;
-  const bool pe_on = is_aux && at < 108, pe_plist = at >= 54;
+  const int pe = at - (NAT - 108);  // entry type of this thread (the last 108 aux threads)
+  const bool pe_on = pe >= 0, pe_plist = pe >= 54;
   if (pe_on) {
-    if (at < 54) {      // P rows (CSC) / P columns (CSR) inside the U lists of node A
-      const int An = s.pu[at][0], m = s.pu[at][1], c2 = s.pu[at][2], p = s.pu[at][3];
+    if (pe < 54) {      // P rows (CSC) / P columns (CSR) inside the U lists of node A
+      const int An = s.pu[pe][0], m = s.pu[pe][1], c2 = s.pu[pe][2], p = s.pu[pe][3];
       const int nd = ga_anode(An, m);
       pe_dx = m & 1; pe_dy = m >> 1;
       pe_li = An * 3 + c2;
       pe_rk = (18 + p) * 30 + c2 * 9 + nd;
       pe_val = (CSR ? 1.0 : -1.0) * s.UP[c2 * 9 + nd][p];
     } else {            // the three P lists of the cell of this quad
-      const int p = (at - 54) / 18, ud = (at - 54) - p * 18;
+      const int p = (pe - 54) / 18, ud = (pe - 54) - p * 18;
       pe_li = 12 + p;
       pe_rk = ud * 30 + 18 + p;
       pe_val = (CSR ? -1.0 : 1.0) * s.UP[ud][p];
@@ -389,7 +398,7 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
             const double w = s.tw[q], gx_ = s.tdx[q][nd], gy_ = s.tdy[q][nd];
             const double ph = w * s.tphi[q][nd], dx = w * gx_, dy = w * gy_;
             const double u0 = u[GS_U0], u1 = u[GS_U1], G00 = u[GS_G00], G01 = u[GS_G01], G10 = u[GS_G10], G11 = u[GS_G11];
-            const double D01 = u[GS_D01], pq = cs[4 * GA_QS + 2 * q], Tq = cs[4 * GA_QS + 2 * q + 1];
+            const double D01 = 0.5 * (G01 + G10), pq = cs[4 * GA_QS + 2 * q], Tq = cs[4 * GA_QS + 2 * q + 1];
             const double m2 = 2.0 * a.Pr * w * u[GS_MUR], bu = a.RaPr * Tq;
             r0 = fma(m2, fma(G00, gx_, D01 * gy_), r0); r0 = fma(ph, fma(u0, G00, u1 * G10) - bu * a.gx, r0); r0 = fma(-dx, pq, r0);
             r1 = fma(m2, fma(D01, gx_, G11 * gy_), r1); r1 = fma(ph, fma(u0, G01, u1 * G11) - bu * a.gy, r1); r1 = fma(-dy, pq, r1);
@@ -481,20 +490,18 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
   // reference-element products of the canonical pair (test node it, trial node jt)
   const int nA = ga_node(ga_ax(A), ga_ay(A)), nB = ga_node(role.bx, role.by);
   const int it = CSR ? nA : nB, jt = CSR ? nB : nA;
-  // (24 + 3 doubles in registers; the viscous products w Pr d_k phi_i d_l phi_j are formed on the fly from the
-  //  gradients, with w Pr jac_scaling folded into the state's mu: 6 extra DFMA per point instead of 32 registers)
-  double TM[4], TP[4], TK;
-  double dix[4], diy[4], djx[4], djy[4];
+  // 29 doubles in registers: the four gradient products, w phi_i phi_j, w phi_i grad phi_j, and the constant TK
+  double PXX[4], PYY[4], PXY[4], PYX[4], TM[4], EX[4], EY[4], TK;
   {
     const CartPairTab &t = a.tab[it * 9 + jt];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      TM[q] = t.TM[q]; TP[q] = t.TP[q];
-      dix[q] = cc.sdx[q][it]; diy[q] = cc.sdy[q][it]; djx[q] = cc.sdx[q][jt]; djy[q] = cc.sdy[q][jt];
+      const double xi = cc.sdx[q][it], yi = cc.sdy[q][it], xj = cc.sdx[q][jt], yj = cc.sdy[q][jt];
+      PXX[q] = xi * xj; PYY[q] = yi * yj; PXY[q] = xi * yj; PYX[q] = yi * xj;
+      TM[q] = t.TM[q]; EX[q] = t.TP[q] * xj; EY[q] = t.TP[q] * yj;
     }
     TK = t.TK;
   }
-
     int xm3 = X0 % 3;
     for (int X = X0 - 4; X < X1; ++X) {
       if (X >= X0 && jac) {
@@ -531,33 +538,24 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
         if (cok && (info & (1u << 19))) {
           const double2 *sp = reinterpret_cast<const double2 *>((mx ? stc1 : stc0) + rr * GA_CS + m * GA_VS);
           const double sg = (m == 1 || m == 2) ? -1.0 : 1.0;
-          double w00 = 0, w01 = 0, w10 = 0, w11 = 0, e = 0;
+          // four independent chains per point (16 per evaluation), summed pairwise at the end
+          double t00[4], t11[4], t01[4], t10[4], eq[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const double2 a0 = sp[q * 6 + 0], a1 = sp[q * 6 + 1], a2 = sp[q * 6 + 2], a3 = sp[q * 6 + 3], a4 = sp[q * 6 + 4],
-                          a5 = sp[q * 6 + 5];  // (mu,G00) (G01,G10) (G11,D01) (dT0,dT1) (sc,u0) (u1,-)
-            {  // viscous: mu' (2 d_x d_x + d_y d_y, d_y phi_i d_x phi_j; d_x phi_i d_y phi_j, d_x d_x + 2 d_y d_y), mu' = jac_scaling w Pr mu
-              const double mu = a0.x;
-              const double pxx = dix[q] * djx[q], pyy = diy[q] * djy[q], pyx = diy[q] * djx[q], pxy = dix[q] * djy[q];
-              w00 = fma(mu, fma(2.0, pxx, pyy), w00); w11 = fma(mu, fma(2.0, pyy, pxx), w11);
-              w01 = fma(mu, pyx, w01); w10 = fma(mu, pxy, w10);
-            }
-            if (!NEWT) {
-              // S_ia = sum_k D[k][a] d_k phi_i (test), S'_jb = sc * S_jb (trial)   
-              const double D01 = a2.y;
-              const double si0 = fma(a0.y, dix[q], D01 * diy[q]), si1 = fma(D01, dix[q], a2.x * diy[q]);
-              const double sj0 = a4.x * fma(a0.y, djx[q], D01 * djy[q]), sj1 = a4.x * fma(D01, djx[q], a2.x * djy[q]);
-              w00 = fma(si0, sj0, w00); w01 = fma(si0, sj1, w01); w10 = fma(si1, sj0, w10); w11 = fma(si1, sj1, w11);
-            }
-            const double cj = fma(a4.y, djx[q], a5.x * djy[q]);  // u . grad phi_j
-            w00 = fma(TM[q], a0.y, w00);
-            w01 = fma(TM[q], a1.y, w01);  // (a=0,b=1): G[1][0]
-            w10 = fma(TM[q], a1.x, w10);  // (a=1,b=0): G[0][1]
-            w11 = fma(TM[q], a2.x, w11);
-            e = fma(TP[q], cj, e);
-            tu0 = fma(TM[q], a3.x, tu0);
-            tu1 = fma(TM[q], a3.y, tu1);
+            const double2 a0 = sp[q * 8 + 0], a1 = sp[q * 8 + 1], a2 = sp[q * 8 + 2], a3 = sp[q * 8 + 3], a4 = sp[q * 8 + 4],
+                          a5 = sp[q * 8 + 5], a6 = sp[q * 8 + 6];  // (A0,A1) (BM,AA) (C1,C2) (G00,G11) (G01,G10) (dT0,dT1) (u0,u1)
+            const double ps = PXY[q] + PYX[q], c1x = a2.x * PXX[q];
+            t00[q] = fma(TM[q], a3.x, fma(a1.x, PYY[q], fma(a2.x, ps, a0.x * PXX[q])));
+            t11[q] = fma(TM[q], a3.y, fma(a0.y, PYY[q], fma(a2.y, ps, a1.x * PXX[q])));
+            t01[q] = fma(TM[q], a4.y, fma(a2.y, PYY[q], fma(a1.x, PYX[q], fma(a1.y, PXY[q], c1x))));  // (a=0,b=1): + w phi phi G[1][0]
+            t10[q] = fma(TM[q], a4.x, fma(a2.y, PYY[q], fma(a1.y, PYX[q], fma(a1.x, PXY[q], c1x))));  // (a=1,b=0): + w phi phi G[0][1]
+            eq[q] = fma(a6.y, EY[q], a6.x * EX[q]);  // w phi_i (u . grad phi_j)
+            tu0 = fma(TM[q], a5.x, tu0);
+            tu1 = fma(TM[q], a5.y, tu1);
           }
+          const double w00 = (t00[0] + t00[1]) + (t00[2] + t00[3]), w11 = (t11[0] + t11[1]) + (t11[2] + t11[3]);
+          const double w01 = (t01[0] + t01[1]) + (t01[2] + t01[3]), w10 = (t10[0] + t10[1]) + (t10[2] + t10[3]);
+          const double e = (eq[0] + eq[1]) + (eq[2] + eq[3]);
           v00 += w00 + e; v11 += w11 + e;
           v01 = fma(sg, w01, v01); v10 = fma(sg, w10, v10);
           tt += e;
