@@ -84,7 +84,12 @@ static inline void gm_cart_fill_tables(const double *rw, const double *rphi, con
 
 // Pair-major copy of the class tables for k_gath: record [class][major node M][minor node m] holds the 9
 // ranks (list k of M) x (dof l of m) at byte k*3+l (bytes 9..15 unused), so a lane fetches them with one
-// 16-byte load.  ctab is [nclass][900] = rank[minor dof][major dof].
+// 16-byte load.  ctab is [nclass][900] = rank[minor dof][major dof].  Entries without a position
+// (Dirichlet minor or major) point at the trash element of the list's staging slot (slot size - 2), so
+// the kernel stores all nine values without a branch.
+static inline int gm_gath_slot_size(int M, int k) {  // staging slot (doubles) of list k of local node M
+  return M < 4 ? (k < 2 ? 90 : 78) : (M < 8 ? (k < 2 ? 54 : 48) : (k < 2 ? 34 : 30));
+}
 static inline void gm_cart_pair_ranks(int nclass, const uint8_t *ctab, uint8_t *ptab) {
   static const int off[3] = {0, 9, 21};
   memset(ptab, 0xFF, (size_t)nclass * 81 * 16);
@@ -92,6 +97,8 @@ static inline void gm_cart_pair_ranks(int nclass, const uint8_t *ctab, uint8_t *
     for (int M = 0; M < 9; ++M)
       for (int m = 0; m < 9; ++m)
         for (int k = 0; k < 3; ++k)
-          for (int l = 0; l < 3; ++l)
-            ptab[((size_t)c * 81 + M * 9 + m) * 16 + k * 3 + l] = ctab[(size_t)c * 900 + (off[l] + m) * 30 + off[k] + M];
+          for (int l = 0; l < 3; ++l) {
+            const uint8_t r = ctab[(size_t)c * 900 + (off[l] + m) * 30 + off[k] + M];
+            ptab[((size_t)c * 81 + M * 9 + m) * 16 + k * 3 + l] = r == 0xFF ? (uint8_t)(gm_gath_slot_size(M, k) - 2) : r;
+          }
 }

@@ -36,7 +36,7 @@
 #define GA_QS 16                   // doubles per (variant, point) state record
 #define GA_VS 72                   // doubles per variant: 4 records + 8 (p, T of the 4 points; variant 0 only); 64 B bank shift
 #define GA_CS (4 * GA_VS + 2)      // doubles per cell (290: consecutive cell rows are shifted by 16 B in the banks)
-#define GA_QSTRIDE 708             // staged doubles per quad: 15 list slots (704) + bank shift
+#define GA_QSTRIDE 732             // staged doubles per quad: 15 list slots (728, gm_gath_slot_size) + bank shift
 
 // State record of one quadrature point (doubles).  The UU block of a node pair is
 //   K_ab = sum_q sum_kl C^ab_kl(q) (d_k phi_i d_l phi_j)(q) + ...   (viscous part + power-law tangent, Solver.jl:131-134)
@@ -164,6 +164,7 @@ struct GaSmem {
   int32_t lg[4][QH][16];             // dof id of each list of quad column X (0: no list / not assembled here)
   int32_t cls[4][NR];
   int16_t slot[16];
+  uint8_t par[4][QH][8];             // parities of the list bases of quad column X (X & 3): [node type | 4 = P] bits k
   uint8_t pu[54][4];                 // (A, m, a, p) of the 54 P-row entries of a quad's U lists
 };
 
@@ -201,7 +202,7 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
   if (tid < 12) { s.twpsi[0][tid] = cc.wpsi[0][tid]; s.tpsi[0][tid] = cc.psi[0][tid]; }
   for (int k = tid; k < 54; k += NT) s.UP[0][k] = cc.UP[0][k];
   if (tid == 0) {
-    const int16_t sl[16] = {0, 88, 176, 252, 304, 356, 402, 454, 506, 552, 584, 616, 644, 664, 684, 704};
+    const int16_t sl[16] = {0, 90, 180, 258, 312, 366, 414, 468, 522, 570, 604, 638, 668, 688, 708, 728};
     for (int k = 0; k < 16; ++k) s.slot[k] = sl[k];
     int n = 0;
     for (int A = 0; A < 4; ++A)
@@ -303,40 +304,51 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
       }
     }
   };
-  // (A4) list records of quad column c: dof id, then (cp.async) list base and end
+  // (A4) list records of quad column c: one thread per (quad row, node type | P lists) = three lists: dof ids,
+  //      then (cp.async) list bases and ends; lists_parity() packs the base parities once they have landed
   auto issue_lists = [&](int c) {
-    for (int k = at; k < QH * 15; k += NAT) {
-      const int rowq = k / 15, li = k - rowq * 15;
-      int32_t g = 0;
-      bool active = false;
-      if (rowq < nqr) {
-        if (li < 12) {
-          const int An = li / 3, kk = li - An * 3;
-          bool found = false;
-          for (int sv = 0; sv < ga_nvar(An); ++sv) {
-            const int m = ga_var(An, sv), cx = c - (m & 1), rr = rowq + 1 - (m >> 1);
-            if (!col_ok(cx) || !row_in_table(rr)) continue;
-            if (row_owned(rr)) active = true;
-            if (!found) {
-              found = true;
-              const int nd = ga_anode(An, m);
-              g = s.gd[cx & 7][rr][kk == 0 ? nd : (kk == 1 ? 9 + nd : 21 + nd)];
-            }
+    if (at >= QH * 5) return;
+    const int rowq = at / 5, grp = at - rowq * 5;
+    int32_t g[3] = {0, 0, 0};
+    bool active = false;
+    if (rowq < nqr) {
+      if (grp < 4) {
+        bool found = false;
+        for (int sv = 0; sv < ga_nvar(grp); ++sv) {
+          const int m = ga_var(grp, sv), cx = c - (m & 1), rr = rowq + 1 - (m >> 1);
+          if (!col_ok(cx) || !row_in_table(rr)) continue;
+          if (row_owned(rr)) active = true;
+          if (!found) {
+            found = true;
+            const int nd = ga_anode(grp, m);
+            const int32_t *gp = &s.gd[cx & 7][rr][0];
+            g[0] = gp[nd]; g[1] = gp[9 + nd]; g[2] = gp[21 + nd];
           }
-        } else if (col_ok(c) && row_owned(rowq + 1)) {
-          active = true;
-          g = s.gd[c & 7][rowq + 1][18 + (li - 12)];
         }
+      } else if (col_ok(c) && row_owned(rowq + 1)) {
+        active = true;
+        const int32_t *gp = &s.gd[c & 7][rowq + 1][18];
+        g[0] = gp[0]; g[1] = gp[1]; g[2] = gp[2];
       }
-      if (!active || g < 0) g = 0;
-      s.lg[c & 3][rowq][li] = g;
-      if (g > 0) {
-        ga_cp8(&s.lbase[c & 3][rowq][li], a.ptr + (g - 1));
-        ga_cp8(&s.lnext[c & 3][rowq][li], a.ptr + g);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int li = grp * 3 + k;
+      const int32_t gk = (active && g[k] > 0) ? g[k] : 0;
+      s.lg[c & 3][rowq][li] = gk;
+      if (gk > 0) {
+        ga_cp8(&s.lbase[c & 3][rowq][li], a.ptr + (gk - 1));
+        ga_cp8(&s.lnext[c & 3][rowq][li], a.ptr + gk);
       } else {
         s.lbase[c & 3][rowq][li] = 0; s.lnext[c & 3][rowq][li] = 0;
       }
     }
+  };
+  auto lists_parity = [&](int c) {  // after this thread's cp.async copies have landed
+    if (at >= QH * 5) return;
+    const int rowq = at / 5, grp = at - rowq * 5;
+    const long long *lb = &s.lbase[c & 3][rowq][grp * 3];
+    s.par[c & 3][rowq][grp] = (uint8_t)((lb[0] & 1) | ((lb[1] & 1) << 1) | ((lb[2] & 1) << 2));
   };
   // (A5) constant P-block entries of quad column X -> staged lists.  Aux thread e < 108 owns entry type e
   //      (everything but the rank class and the list parity is loop invariant) and walks the quad rows.
@@ -376,7 +388,7 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
 #pragma unroll
     for (int rowq = 0; rowq < QH; ++rowq) {
       if (rk[rowq] == 0xFF) continue;
-      const int par = (int)(s.lbase[X & 3][rowq][pe_li] & 1);
+      const int par = (s.par[X & 3][rowq][pe_li / 3] >> (pe_li % 3)) & 1;
       stg0[rowq * GA_QSTRIDE + par + rk[rowq]] = own[rowq] ? pe_val : 0.0;
     }
   };
@@ -458,6 +470,7 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
       if (live && res) residual(X);
       state(X + 1);
       ga_cp_wait_all();
+      if (X + 1 >= X0 && X + 1 < X1) lists_parity(X + 1);
       ga_bulk_wait_read();
       ga_fence_async();
       ga_bar_step<NT>();  // lists of column X staged, state of X+1 ready, asynchronous copies landed
@@ -513,17 +526,12 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
       bool have = false;
       // rank records of the four rounds and list parities of the flushing rounds: all loads up front
       uint4 rec[4];
-      uint32_t parm = 0;
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const uint32_t info = R[r];
         const int cx = X - (int)((info >> 4) & 1);
         if (cx >= 0 && cx < a.nx && (info & (1u << 18)))
           rec[r] = GA_LDG(reinterpret_cast<const uint4 *>(a.ptab) + ((int64_t)s.cls[cx & 3][info & 15] * 81 + ((info >> 11) & 127)));
-        if (info & (1u << 6)) {
-          const int *lb = reinterpret_cast<const int *>(&s.lbase[X & 3][(info >> 7) & 15][A * 3]);
-          parm |= (uint32_t)((lb[0] & 1) | ((lb[2] & 1) << 1) | ((lb[4] & 1) << 2)) << (3 * r);
-        }
       }
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
@@ -565,8 +573,8 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
           if (have) {
             const int rowq = (info >> 7) & 15;
             double *q0 = stg0 + rowq * GA_QSTRIDE;
-            const uint32_t pm = parm >> (3 * r);
-            const int slot0 = A == 0 ? 0 : (A == 1 ? 252 : (A == 2 ? 402 : 552)), slen = A == 0 ? 88 : (A == 3 ? 32 : 52);
+            const uint32_t pm = s.par[X & 3][rowq][A];
+            const int slot0 = A == 0 ? 0 : (A == 1 ? 258 : (A == 2 ? 414 : 570)), slen = A == 0 ? 90 : (A == 3 ? 34 : 54);
             double *b0 = q0 + slot0 + (pm & 1), *b1 = q0 + slot0 + slen + ((pm >> 1) & 1), *b2 = q0 + slot0 + 2 * slen + ((pm >> 2) & 1);
             // constant parts: nev * (TK ; buoyancy -Ra Pr g_a sum_q w phi_i phi_j)
             const double cn = (double)nev, mb = cn * ((TM[0] + TM[1]) + (TM[2] + TM[3]));
@@ -576,15 +584,15 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
             if (CSR) { e00 = v00; e01 = v01; e02 = ut0; e10 = v10; e11 = v11; e12 = ut1; e20 = tu0; e21 = tu1; e22 = tt; }
             else     { e00 = v00; e01 = v10; e02 = tu0; e10 = v01; e11 = v11; e12 = tu1; e20 = ut0; e21 = ut1; e22 = tt; }
             int rk;
-            rk = rk0 & 255;         if (rk != 255) b0[rk] = e00;
-            rk = (rk0 >> 8) & 255;  if (rk != 255) b0[rk] = e01;
-            rk = (rk0 >> 16) & 255; if (rk != 255) b0[rk] = e02;
-            rk = rk0 >> 24;         if (rk != 255) b1[rk] = e10;
-            rk = rk1 & 255;         if (rk != 255) b1[rk] = e11;
-            rk = (rk1 >> 8) & 255;  if (rk != 255) b1[rk] = e12;
-            rk = (rk1 >> 16) & 255; if (rk != 255) b2[rk] = e20;
-            rk = rk1 >> 24;         if (rk != 255) b2[rk] = e21;
-            rk = rk2 & 255;         if (rk != 255) b2[rk] = e22;
+            rk = rk0 & 255; b0[rk] = e00;
+            rk = (rk0 >> 8) & 255; b0[rk] = e01;
+            rk = (rk0 >> 16) & 255; b0[rk] = e02;
+            rk = rk0 >> 24; b1[rk] = e10;
+            rk = rk1 & 255; b1[rk] = e11;
+            rk = (rk1 >> 8) & 255; b1[rk] = e12;
+            rk = (rk1 >> 16) & 255; b2[rk] = e20;
+            rk = rk1 >> 24; b2[rk] = e21;
+            rk = rk2 & 255; b2[rk] = e22;
           }
           v00 = v01 = v10 = v11 = tu0 = tu1 = tt = 0;
           nev = 0;
