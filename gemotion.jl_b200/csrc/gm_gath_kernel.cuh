@@ -158,6 +158,7 @@ struct GaSmem {
   double visc[4][NR][4][2];
   long long lbase[4][QH][16];        // list bases / ends of quad column X (X & 3); 15 used
   long long lnext[4][QH][16];
+  double ltk[3 * NG * 32];           // per matrix lane: TK of its node pair
   double tphi[4][9], tdx[4][9], tdy[4][9], tw[4], twpsi[4][3], tpsi[4][3];
   double UP[18][3];
   int32_t gd[8][NR][30];             // dof ids of cell column c (c & 7)
@@ -503,8 +504,8 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
   // reference-element products of the canonical pair (test node it, trial node jt)
   const int nA = ga_node(ga_ax(A), ga_ay(A)), nB = ga_node(role.bx, role.by);
   const int it = CSR ? nA : nB, jt = CSR ? nB : nA;
-  // 29 doubles in registers: the four gradient products, w phi_i phi_j, w phi_i grad phi_j, and the constant TK
-  double PXX[4], PYY[4], PXY[4], PYX[4], TM[4], EX[4], EY[4], TK;
+  // 28 doubles in registers: the four gradient products, w phi_i phi_j, w phi_i grad phi_j, and the constant TK
+  double PXX[4], PYY[4], PXY[4], PYX[4], TM[4], EX[4], EY[4];  // (TK is used once per flush: parked in shared memory)
   {
     const CartPairTab &t = a.tab[it * 9 + jt];
 #pragma unroll
@@ -513,8 +514,9 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
       PXX[q] = xi * xj; PYY[q] = yi * yj; PXY[q] = xi * yj; PYX[q] = yi * xj;
       TM[q] = t.TM[q]; EX[q] = t.TP[q] * xj; EY[q] = t.TP[q] * yj;
     }
-    TK = t.TK;
+    s.ltk[tid] = t.TK;
   }
+    const int slotpk = (A == 0 ? 0 : (A == 1 ? 258 : (A == 2 ? 414 : 570))) | ((A == 0 ? 90 : (A == 3 ? 34 : 54)) << 16);
     int xm3 = X0 % 3;
     for (int X = X0 - 4; X < X1; ++X) {
       if (X >= X0 && jac) {
@@ -524,46 +526,49 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
         int nev = 0;  // cells summed into the current output (constant parts are added at the flush)
       uint32_t rk0 = 0, rk1 = 0, rk2 = 0;
       bool have = false;
-      // rank records of the four rounds and list parities of the flushing rounds: all loads up front
-      uint4 rec[4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
+      // rank record of a round: loaded one round ahead (the first one before round 0)
+      auto load_rec = [&](int r) -> uint4 {
         const uint32_t info = R[r];
         const int cx = X - (int)((info >> 4) & 1);
+        uint4 v = {0, 0, 0, 0};
         if (cx >= 0 && cx < a.nx && (info & (1u << 18)))
-          rec[r] = GA_LDG(reinterpret_cast<const uint4 *>(a.ptab) + ((int64_t)s.cls[cx & 3][info & 15] * 81 + ((info >> 11) & 127)));
-      }
+          v = GA_LDG(reinterpret_cast<const uint4 *>(a.ptab) + ((int64_t)s.cls[cx & 3][info & 15] * 81 + ((info >> 11) & 127)));
+        return v;
+      };
+      uint4 rec_nxt = load_rec(0);
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const uint32_t info = R[r];
         const int rr = info & 15, m = (info >> 4) & 3, mx = m & 1;
         const int cx = X - mx;
         const bool cok = cx >= 0 && cx < a.nx;
+        const uint4 rec_cur = rec_nxt;
+        if (r < 3) rec_nxt = load_rec(r + 1);
         if (cok && (info & (1u << 18))) {
-          rk0 = rec[r].x; rk1 = rec[r].y; rk2 = rec[r].z;
+          rk0 = rec_cur.x; rk1 = rec_cur.y; rk2 = rec_cur.z;
           have = true;
         }
         if (cok && (info & (1u << 19))) {
           const double2 *sp = reinterpret_cast<const double2 *>((mx ? stc1 : stc0) + rr * GA_CS + m * GA_VS);
           const double sg = (m == 1 || m == 2) ? -1.0 : 1.0;
-          // four independent chains per point (16 per evaluation), summed pairwise at the end
-          double t00[4], t11[4], t01[4], t10[4], eq[4];
+          // two independent chains per output (points 0,1 and 2,3): 10 chains per evaluation
+          double t00[2] = {0, 0}, t11[2] = {0, 0}, t01[2] = {0, 0}, t10[2] = {0, 0}, eq[2] = {0, 0};
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
+            const int h = q >> 1;
             const double2 a0 = sp[q * 8 + 0], a1 = sp[q * 8 + 1], a2 = sp[q * 8 + 2], a3 = sp[q * 8 + 3], a4 = sp[q * 8 + 4],
                           a5 = sp[q * 8 + 5], a6 = sp[q * 8 + 6];  // (A0,A1) (BM,AA) (C1,C2) (G00,G11) (G01,G10) (dT0,dT1) (u0,u1)
             const double ps = PXY[q] + PYX[q], c1x = a2.x * PXX[q];
-            t00[q] = fma(TM[q], a3.x, fma(a1.x, PYY[q], fma(a2.x, ps, a0.x * PXX[q])));
-            t11[q] = fma(TM[q], a3.y, fma(a0.y, PYY[q], fma(a2.y, ps, a1.x * PXX[q])));
-            t01[q] = fma(TM[q], a4.y, fma(a2.y, PYY[q], fma(a1.x, PYX[q], fma(a1.y, PXY[q], c1x))));  // (a=0,b=1): + w phi phi G[1][0]
-            t10[q] = fma(TM[q], a4.x, fma(a2.y, PYY[q], fma(a1.y, PYX[q], fma(a1.x, PXY[q], c1x))));  // (a=1,b=0): + w phi phi G[0][1]
-            eq[q] = fma(a6.y, EY[q], a6.x * EX[q]);  // w phi_i (u . grad phi_j)
+            t00[h] = fma(TM[q], a3.x, fma(a1.x, PYY[q], fma(a2.x, ps, fma(a0.x, PXX[q], t00[h]))));
+            t11[h] = fma(TM[q], a3.y, fma(a0.y, PYY[q], fma(a2.y, ps, fma(a1.x, PXX[q], t11[h]))));
+            t01[h] = fma(TM[q], a4.y, fma(a2.y, PYY[q], fma(a1.x, PYX[q], fma(a1.y, PXY[q], c1x + t01[h]))));  // (a=0,b=1): + w phi phi G[1][0]
+            t10[h] = fma(TM[q], a4.x, fma(a2.y, PYY[q], fma(a1.y, PYX[q], fma(a1.x, PXY[q], c1x + t10[h]))));  // (a=1,b=0): + w phi phi G[0][1]
+            eq[h] = fma(a6.y, EY[q], fma(a6.x, EX[q], eq[h]));  // w phi_i (u . grad phi_j)
             tu0 = fma(TM[q], a5.x, tu0);
             tu1 = fma(TM[q], a5.y, tu1);
           }
-          const double w00 = (t00[0] + t00[1]) + (t00[2] + t00[3]), w11 = (t11[0] + t11[1]) + (t11[2] + t11[3]);
-          const double w01 = (t01[0] + t01[1]) + (t01[2] + t01[3]), w10 = (t10[0] + t10[1]) + (t10[2] + t10[3]);
-          const double e = (eq[0] + eq[1]) + (eq[2] + eq[3]);
+          const double w00 = t00[0] + t00[1], w11 = t11[0] + t11[1], w01 = t01[0] + t01[1], w10 = t10[0] + t10[1];
+          const double e = eq[0] + eq[1];
           v00 += w00 + e; v11 += w11 + e;
           v01 = fma(sg, w01, v01); v10 = fma(sg, w10, v10);
           tt += e;
@@ -574,12 +579,12 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
             const int rowq = (info >> 7) & 15;
             double *q0 = stg0 + rowq * GA_QSTRIDE;
             const uint32_t pm = s.par[X & 3][rowq][A];
-            const int slot0 = A == 0 ? 0 : (A == 1 ? 258 : (A == 2 ? 414 : 570)), slen = A == 0 ? 90 : (A == 3 ? 34 : 54);
+            const int slot0 = slotpk & 0xFFFF, slen = slotpk >> 16;
             double *b0 = q0 + slot0 + (pm & 1), *b1 = q0 + slot0 + slen + ((pm >> 1) & 1), *b2 = q0 + slot0 + 2 * slen + ((pm >> 2) & 1);
             // constant parts: nev * (TK ; buoyancy -Ra Pr g_a sum_q w phi_i phi_j)
             const double cn = (double)nev, mb = cn * ((TM[0] + TM[1]) + (TM[2] + TM[3]));
             const double ut0 = -a.RaPr * a.gx * mb, ut1 = -a.RaPr * a.gy * mb;
-            tt = fma(cn, TK, tt);
+            tt = fma(cn, s.ltk[tid], tt);
             double e00, e01, e02, e10, e11, e12, e20, e21, e22;  // [list k][minor dof l]
             if (CSR) { e00 = v00; e01 = v01; e02 = ut0; e10 = v10; e11 = v11; e12 = ut1; e20 = tu0; e21 = tu1; e22 = tt; }
             else     { e00 = v00; e01 = v10; e02 = tu0; e10 = v01; e11 = v11; e12 = tu1; e20 = ut0; e21 = ut1; e22 = tt; }
