@@ -225,10 +225,16 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
   // =====================================================================================
   // aux tasks
   // =====================================================================================
+  // Work split over the six aux warps (w0..w5; per-task warp-instruction counts from the ncu source view):
+  //   dof ids / values : second pass on w3..w5      list records : w0, w1       state : velocity w2, w3; T w0, w1; p w4, w5
+  //   P entries, write-out : w0, w1, w4, w5         residual : w2..w5
+  static_assert(NAT == 192, "the aux task split below assumes six aux warps");
+  const int at_hi = NAT - 1 - at;                              // item order for the two-pass loops
+  const int at_o = at < 64 ? at : (at >= 128 ? at - 64 : -1);  // 0..127 on w0, w1, w4, w5
   // (A1) dof ids of cell column c
   auto issue_gd = [&](int c) {
     if (!col_ok(c)) return;
-    for (int k = at; k < NR * 30; k += NAT) {
+    for (int k = at_hi; k < NR * 30; k += NAT) {
       const int rr = k / 30, l = k - rr * 30;
       if (!row_in_table(rr)) continue;
       ga_cp4(&s.gd[c & 7][rr][l], a.gdofs + ((int64_t)(Yc0 + rr) * a.nx + c) * 30 + l);
@@ -237,7 +243,7 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
   // (A2) iterate values, viscosity, rank class of cell column c (its dof ids have landed)
   auto issue_val = [&](int c) {
     if (!col_ok(c)) return;
-    for (int k = at; k < NR * 30; k += NAT) {
+    for (int k = at_hi; k < NR * 30; k += NAT) {
       const int rr = k / 30, l = k - rr * 30;
       if (!row_in_table(rr)) continue;
       const int32_t d = s.gd[c & 7][rr][l];
@@ -256,7 +262,7 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
     if (!col_ok(c)) return;
     double *sc0 = s.st[c % 3];
     for (int k0 = at; k0 < 3 * 64; k0 += NAT) {  // g-major item order: a warp runs one kind of item;
-      const int k = (k0 + 64) % 192;              // the velocity items go to the warps without residual work
+      const int k = k0 < 64 ? k0 + 64 : (k0 < 128 ? k0 - 64 : k0);  // velocity items (0..63) on w2, w3
       const int g = k >> 6, e = k & 63, rr = e >> 2, q = e & 3;
       if (rr >= NR || !row_owned(rr)) continue;
       double *cs = sc0 + rr * GA_CS;
@@ -355,8 +361,8 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
   //      (everything but the rank class and the list parity is loop invariant) and walks the quad rows.
   int pe_li = 0, pe_rk = 0, pe_dx = 0, pe_dy = 0;
   double pe_val = 0.0;
-  const int pe = at - (NAT - 108);  // entry type of this thread (the last 108 aux threads)
-  const bool pe_on = pe >= 0, pe_plist = pe >= 54;
+  const int pe = at_o;  // entry type of this thread
+  const bool pe_on = pe >= 0 && pe < 108, pe_plist = pe >= 54;
   if (pe_on) {
     if (pe < 54) {      // P rows (CSC) / P columns (CSR) inside the U lists of node A
       const int An = s.pu[pe][0], m = s.pu[pe][1], c2 = s.pu[pe][2], p = s.pu[pe][3];
@@ -397,8 +403,8 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
   //      are combined by two butterfly shuffles, lane 0 of the quartet stores the three dofs of the node
   auto residual = [&](int X) {
     for (int k0 = 0; k0 < QH * 16; k0 += NAT) {  // (NAT is a multiple of 32: whole warps enter together)
-      const int k = k0 + at;
-      const int rowq = k >> 4, An = (k >> 2) & 3, sv = k & 3;
+      const int k = k0 + at - 64;  // (w2..w5; negative on w0, w1: no item)
+      const int rowq = k < 0 ? QH : (k >> 4), An = (k >> 2) & 3, sv = k & 3;
       double r0 = 0, r1 = 0, r2 = 0;
       if (rowq < nqr && sv < ga_nvar(An)) {
         const int m = ga_var(An, sv), cx = X - (m & 1), rr = rowq + 1 - (m >> 1);
@@ -428,7 +434,7 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
         if (lg[2] > 0) a.b[lg[2] - 1] = r2;
       }
     }
-    for (int k = at; k < QH * 3; k += NAT) {  // pressure rows: cell-local
+    for (int k = at - 64; k >= 0 && k < QH * 3; k += NAT) {  // pressure rows: cell-local
       const int rowq = k / 3, p = k - rowq * 3;
       if (rowq >= nqr) break;
       const int32_t g = s.lg[X & 3][rowq][12 + p];
@@ -444,7 +450,7 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
   auto write_out = [&](int X) {
     ga_fence_async();
     const double *stg0 = s.stage[X & 1];
-    for (int k = at; k < QH * 15; k += NAT) {
+    for (int k = at_o; k >= 0 && k < QH * 15; k += NAT) {
       const int rowq = k / 15, li = k - rowq * 15;
       if (rowq >= nqr) break;
       if (s.lg[X & 3][rowq][li] <= 0) continue;
