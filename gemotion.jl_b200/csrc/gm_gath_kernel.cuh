@@ -159,7 +159,6 @@ struct GaSmem {
   long long lbase[4][QH][16];        // list bases / ends of quad column X (X & 3); 15 used
   long long lnext[4][QH][16];
   double ltk[3 * NG * 32];           // per matrix lane: TK of its node pair
-  double trash[3 * NG * 32];         // per matrix lane: target of the stores of a round without output
   double tphi[4][9], tdx[4][9], tdy[4][9], tw[4], twpsi[4][3], tpsi[4][3];
   double UP[18][3];
   int32_t gd[8][NR][30];             // dof ids of cell column c (c & 7)
@@ -533,35 +532,33 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
         int nev = 0;  // cells summed into the current output (constant parts are added at the flush)
       uint32_t rk0 = 0, rk1 = 0, rk2 = 0;
       bool have = false;
-      // The four rounds are straight-line code (no branch on the per-lane validity / flush bits: results are
-      // selected, stores of idle lanes go to a per-thread trash element), so that the loads of a round can be
-      // scheduled into the arithmetic of the previous one.
-      auto load_rec = [&](int r) -> uint4 {  // rank record of round r (record 0 of class 0 for a lane without a cell)
+      // rank record of a round: loaded one round ahead (the first one before round 0)
+      auto load_rec = [&](int r) -> uint4 {
         const uint32_t info = R[r];
         const int cx = X - (int)((info >> 4) & 1);
-        const bool ok = cx >= 0 && cx < a.nx && (info & (1u << 18));
-        const int64_t ridx = ok ? (int64_t)s.cls[cx & 3][info & 15] * 81 + ((info >> 11) & 127) : 0;
-        return GA_LDG(reinterpret_cast<const uint4 *>(a.ptab) + ridx);
+        uint4 v = {0, 0, 0, 0};
+        if (cx >= 0 && cx < a.nx && (info & (1u << 18)))
+          v = GA_LDG(reinterpret_cast<const uint4 *>(a.ptab) + ((int64_t)s.cls[cx & 3][info & 15] * 81 + ((info >> 11) & 127)));
+        return v;
       };
       uint4 rec_nxt = load_rec(0);
-      double *const trash = &s.trash[tid];
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const uint32_t info = R[r];
         const int rr = info & 15, m = (info >> 4) & 3, mx = m & 1;
         const int cx = X - mx;
         const bool cok = cx >= 0 && cx < a.nx;
-        const bool in_tab = cok && (info & (1u << 18)), owned = cok && (info & (1u << 19)), flush = (info & (1u << 6)) != 0;
         const uint4 rec_cur = rec_nxt;
         if (r < 3) rec_nxt = load_rec(r + 1);
-        rk0 = in_tab ? rec_cur.x : rk0; rk1 = in_tab ? rec_cur.y : rk1; rk2 = in_tab ? rec_cur.z : rk2;
-        have = have || in_tab;
-        {
-          // (a lane without an owned cell reads whatever its state slot holds and drops the result)
+        if (cok && (info & (1u << 18))) {
+          rk0 = rec_cur.x; rk1 = rec_cur.y; rk2 = rec_cur.z;
+          have = true;
+        }
+        if (cok && (info & (1u << 19))) {
           const double2 *sp = reinterpret_cast<const double2 *>((mx ? stc1 : stc0) + rr * GA_CS + m * GA_VS);
           const double sg = (m == 1 || m == 2) ? -1.0 : 1.0;
           // two independent chains per output (points 0,1 and 2,3): 10 chains per evaluation
-          double t00[2] = {0, 0}, t11[2] = {0, 0}, t01[2] = {0, 0}, t10[2] = {0, 0}, eq[2] = {0, 0}, tv0[2] = {0, 0}, tv1[2] = {0, 0};
+          double t00[2] = {0, 0}, t11[2] = {0, 0}, t01[2] = {0, 0}, t10[2] = {0, 0}, eq[2] = {0, 0};
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int h = q >> 1;
@@ -573,38 +570,44 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
             t01[h] = fma(TM[q], a4.y, fma(a2.y, PYY[q], fma(a1.x, PYX[q], fma(a1.y, PXY[q], c1x + t01[h]))));  // (a=0,b=1): + w phi phi G[1][0]
             t10[h] = fma(TM[q], a4.x, fma(a2.y, PYY[q], fma(a1.y, PYX[q], fma(a1.x, PXY[q], c1x + t10[h]))));  // (a=1,b=0): + w phi phi G[0][1]
             eq[h] = fma(a6.y, EY[q], fma(a6.x, EX[q], eq[h]));  // w phi_i (u . grad phi_j)
-            tv0[h] = fma(TM[q], a5.x, tv0[h]);
-            tv1[h] = fma(TM[q], a5.y, tv1[h]);
+            tu0 = fma(TM[q], a5.x, tu0);
+            tu1 = fma(TM[q], a5.y, tu1);
           }
+          const double w00 = t00[0] + t00[1], w11 = t11[0] + t11[1], w01 = t01[0] + t01[1], w10 = t10[0] + t10[1];
           const double e = eq[0] + eq[1];
-          const double w00 = (t00[0] + t00[1]) + e, w11 = (t11[0] + t11[1]) + e, w01 = sg * (t01[0] + t01[1]), w10 = sg * (t10[0] + t10[1]);
-          v00 += owned ? w00 : 0.0; v11 += owned ? w11 : 0.0; v01 += owned ? w01 : 0.0; v10 += owned ? w10 : 0.0;
-          tu0 += owned ? tv0[0] + tv0[1] : 0.0; tu1 += owned ? tv1[0] + tv1[1] : 0.0; tt += owned ? e : 0.0;
-          nev += owned ? 1 : 0;
+          v00 += w00 + e; v11 += w11 + e;
+          v01 = fma(sg, w01, v01); v10 = fma(sg, w10, v10);
+          tt += e;
+          ++nev;
         }
-        {
-          const bool st = flush && have;
-          const int rowq = (info >> 7) & 15;
-          double *q0 = stg0 + rowq * GA_QSTRIDE;
-          const uint32_t pm = s.par[X & 3][rowq][A];
-          const int slot0 = slotpk & 0xFFFF, slen = slotpk >> 16;
-          double *b0 = st ? q0 + slot0 + (pm & 1) : trash, *b1 = st ? q0 + slot0 + slen + ((pm >> 1) & 1) : trash,
-                 *b2 = st ? q0 + slot0 + 2 * slen + ((pm >> 2) & 1) : trash;
-          const uint32_t r0 = st ? rk0 : 0u, r1 = st ? rk1 : 0u, r2 = st ? rk2 : 0u;
-          // constant parts: nev * (TK ; buoyancy -Ra Pr g_a sum_q w phi_i phi_j)
-          const double cn = (double)nev, mb = cn * ((TM[0] + TM[1]) + (TM[2] + TM[3]));
-          const double ut0 = -a.RaPr * a.gx * mb, ut1 = -a.RaPr * a.gy * mb;
-          const double ttc = fma(cn, s.ltk[tid], tt);
-          double e00, e01, e02, e10, e11, e12, e20, e21, e22;  // [list k][minor dof l]
-          if (CSR) { e00 = v00; e01 = v01; e02 = ut0; e10 = v10; e11 = v11; e12 = ut1; e20 = tu0; e21 = tu1; e22 = ttc; }
-          else     { e00 = v00; e01 = v10; e02 = tu0; e10 = v01; e11 = v11; e12 = tu1; e20 = ut0; e21 = ut1; e22 = ttc; }
-          b0[r0 & 255] = e00; b0[(r0 >> 8) & 255] = e01; b0[(r0 >> 16) & 255] = e02;
-          b1[r0 >> 24] = e10; b1[r1 & 255] = e11; b1[(r1 >> 8) & 255] = e12;
-          b2[(r1 >> 16) & 255] = e20; b2[r1 >> 24] = e21; b2[r2 & 255] = e22;
-          v00 = flush ? 0.0 : v00; v01 = flush ? 0.0 : v01; v10 = flush ? 0.0 : v10; v11 = flush ? 0.0 : v11;
-          tu0 = flush ? 0.0 : tu0; tu1 = flush ? 0.0 : tu1; tt = flush ? 0.0 : tt;
-          nev = flush ? 0 : nev;
-          have = have && !flush;
+        if (info & (1u << 6)) {
+          if (have) {
+            const int rowq = (info >> 7) & 15;
+            double *q0 = stg0 + rowq * GA_QSTRIDE;
+            const uint32_t pm = s.par[X & 3][rowq][A];
+            const int slot0 = slotpk & 0xFFFF, slen = slotpk >> 16;
+            double *b0 = q0 + slot0 + (pm & 1), *b1 = q0 + slot0 + slen + ((pm >> 1) & 1), *b2 = q0 + slot0 + 2 * slen + ((pm >> 2) & 1);
+            // constant parts: nev * (TK ; buoyancy -Ra Pr g_a sum_q w phi_i phi_j)
+            const double cn = (double)nev, mb = cn * ((TM[0] + TM[1]) + (TM[2] + TM[3]));
+            const double ut0 = -a.RaPr * a.gx * mb, ut1 = -a.RaPr * a.gy * mb;
+            tt = fma(cn, s.ltk[tid], tt);
+            double e00, e01, e02, e10, e11, e12, e20, e21, e22;  // [list k][minor dof l]
+            if (CSR) { e00 = v00; e01 = v01; e02 = ut0; e10 = v10; e11 = v11; e12 = ut1; e20 = tu0; e21 = tu1; e22 = tt; }
+            else     { e00 = v00; e01 = v10; e02 = tu0; e10 = v01; e11 = v11; e12 = tu1; e20 = ut0; e21 = ut1; e22 = tt; }
+            int rk;
+            rk = rk0 & 255; b0[rk] = e00;
+            rk = (rk0 >> 8) & 255; b0[rk] = e01;
+            rk = (rk0 >> 16) & 255; b0[rk] = e02;
+            rk = rk0 >> 24; b1[rk] = e10;
+            rk = rk1 & 255; b1[rk] = e11;
+            rk = (rk1 >> 8) & 255; b1[rk] = e12;
+            rk = (rk1 >> 16) & 255; b2[rk] = e20;
+            rk = rk1 >> 24; b2[rk] = e21;
+            rk = rk2 & 255; b2[rk] = e22;
+          }
+          v00 = v01 = v10 = v11 = tu0 = tu1 = tt = 0;
+          nev = 0;
+          have = false;
         }
       }
       ga_fence_async();  // staged entries -> visible to the TMA (async proxy) reads of the next step
