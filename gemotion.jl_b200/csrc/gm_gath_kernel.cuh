@@ -30,7 +30,7 @@
 // index logic can be checked against the oracle without a GPU (tests/test_gath_emu.py).
 #pragma once
 
-#define GA_XCH 128                 // quad columns per x-chunk
+#define GA_XCH 256                 // quad columns per x-chunk
 #define GA_NAUX 6                  // aux warps
 #define GA_MAXREG 168               // 65536 / (12 warps * 32): warps are allocated in fours
 #define GA_QS 16                   // doubles per (variant, point) state record
@@ -92,12 +92,8 @@ __device__ __forceinline__ void ga_bulk_commit() { asm volatile("cp.async.bulk.c
 __device__ __forceinline__ void ga_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void ga_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ double ga_shfl_xor(double v, int mask) { return __shfl_xor_sync(0xffffffffu, v, mask); }
-// producer / consumer barriers between the two role loops: `id` = 2, 3 "aux finished step X" (X & 1), 4, 5 "matrix
-// finished step X".  The finishing role arrives (does not wait), the other role syncs.
 template <int NT>
-__device__ __forceinline__ void ga_bar_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(NT) : "memory"); }
-template <int NT>
-__device__ __forceinline__ void ga_bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NT) : "memory"); }
+__device__ __forceinline__ void ga_bar_step() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }  // both role loops meet here
 #endif
 
 // local node index of the tensor position (ix, iy) of a Q2 cell (same table as c_ct_node)
@@ -156,7 +152,7 @@ __host__ __device__ __forceinline__ int ga_anode(int A, int m) {
 template <int NG>
 struct GaSmem {
   static constexpr int QH = 4 * NG, NR = QH + 1;
-  double st[4][NR * GA_CS];          // state ring (cell column & 3): columns X-1, X in use, X+1 / X+2 being built
+  double st[3][NR * GA_CS];          // state ring (cell column mod 3)
   double stage[2][QH * GA_QSTRIDE];  // staged lists of quad column X (X & 1)
   double val[4][NR][30];             // iterate values of cell column c (c & 3)
   double visc[4][NR][4][2];
@@ -167,7 +163,7 @@ struct GaSmem {
   double UP[18][3];
   int32_t gd[8][NR][30];             // dof ids of cell column c (c & 7)
   int32_t lg[4][QH][16];             // dof id of each list of quad column X (0: no list / not assembled here)
-  int32_t cls[8][NR];                // rank class of cell column c (c & 7)
+  int32_t cls[4][NR];
   int16_t slot[16];
   uint8_t par[4][QH][8];             // parities of the list bases of quad column X (X & 3): [node type | 4 = P] bits k
   uint8_t pu[54][4];                 // (A, m, a, p) of the 54 P-row entries of a quad's U lists
@@ -258,13 +254,13 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
       if (!row_in_table(rr)) continue;
       const int64_t cell = (int64_t)(Yc0 + rr) * a.nx + c;
       if (!NEWT) ga_cp16(&s.visc[c & 3][rr][q][0], a.visc + (cell * 4 + q) * 2);
-      if (q == 0) ga_cp4(&s.cls[c & 7][rr], a.cls + cell);
+      if (q == 0) ga_cp4(&s.cls[c & 3][rr], a.cls + cell);
     }
   };
   // (A3) state of cell column c: fields at the quadrature points, four mirror variants
   auto state = [&](int c) {
     if (!col_ok(c)) return;
-    double *sc0 = s.st[c & 3];
+    double *sc0 = s.st[c % 3];
     for (int k0 = at; k0 < 3 * 64; k0 += NAT) {  // g-major item order: a warp runs one kind of item;
       const int k = k0 < 64 ? k0 + 64 : (k0 < 128 ? k0 - 64 : k0);  // velocity items (0..63) on w2, w3
       const int g = k >> 6, e = k & 63, rr = e >> 2, q = e & 3;
@@ -394,7 +390,7 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
       const int rr = rowq + 1 - pe_dy;
       own[rowq] = row_owned(rr);
       const bool ok = rowq < nqr && row_in_table(rr) && (own[rowq] || !pe_plist);
-      rk[rowq] = ok ? (int)GA_LDG(a.ctab + (int64_t)s.cls[cx & 7][ok ? rr : 0] * 900 + pe_rk) : 0xFF;
+      rk[rowq] = ok ? (int)GA_LDG(a.ctab + (int64_t)s.cls[cx & 3][ok ? rr : 0] * 900 + pe_rk) : 0xFF;
     }
 #pragma unroll
     for (int rowq = 0; rowq < QH; ++rowq) {
@@ -414,7 +410,7 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
         const int m = ga_var(An, sv), cx = X - (m & 1), rr = rowq + 1 - (m >> 1);
         if (col_ok(cx) && row_owned(rr)) {
           const int nd = ga_anode(An, m);
-          const double *cs = s.st[cx & 3] + rr * GA_CS;
+          const double *cs = s.st[cx % 3] + rr * GA_CS;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const double *u = cs + q * GA_QS;
@@ -443,7 +439,7 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
       if (rowq >= nqr) break;
       const int32_t g = s.lg[X & 3][rowq][12 + p];
       if (g <= 0) continue;
-      const double *cs = s.st[X & 3] + (rowq + 1) * GA_CS;
+      const double *cs = s.st[X % 3] + (rowq + 1) * GA_CS;
       double v = 0;
 #pragma unroll
       for (int q = 0; q < 4; ++q) v += s.twpsi[q][p] * (cs[q * GA_QS + GS_G00] + cs[q * GA_QS + GS_G11]);
@@ -471,26 +467,21 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
     ga_bulk_commit();
   };
 
-    // Step X of the aux role.  Everything up to the sync only needs earlier aux work, so it overlaps the matrix
-    // role's step X-1; the write-out of column X-1 waits for it.  The sync is also the aux-internal barrier
-    // between the steps (landed dof ids / values / states of one step are read by other aux threads in the next).
     for (int X = X0 - 4; X < X1; ++X) {
       const bool live = X >= X0;
+      if (live && X > X0 && jac) write_out(X - 1);
       issue_gd(X + 3);
       issue_val(X + 2);
       if (X + 1 >= X0 && X + 1 < X1) issue_lists(X + 1);
+      if (live && jac) p_entries(X);
       if (live && res) residual(X);
       state(X + 1);
       ga_cp_wait_all();
       if (X + 1 >= X0 && X + 1 < X1) lists_parity(X + 1);
-      if (X > X0 - 4) ga_bar_sync<NT>(4 + ((X - 1) & 1));  // matrix finished step X-1
-      if (live && X > X0 && jac) write_out(X - 1);
-      if (live && jac) p_entries(X);
       ga_bulk_wait_read();
       ga_fence_async();
-      ga_bar_arrive<NT>(2 + (X & 1));  // aux finished step X: state / lists of X+1 ready, stage[(X-1)&1] drained
+      ga_bar_step<NT>();  // lists of column X staged, state of X+1 ready, asynchronous copies landed
     }
-    ga_bar_sync<NT>(4 + ((X1 - 1) & 1));
     if (jac) {  // last column of the chunk
       write_out(X1 - 1);
       ga_bulk_wait_read();
@@ -532,10 +523,10 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
     s.ltk[tid] = t.TK;
   }
     const int slotpk = (A == 0 ? 0 : (A == 1 ? 258 : (A == 2 ? 414 : 570))) | ((A == 0 ? 90 : (A == 3 ? 34 : 54)) << 16);
+    int xm3 = X0 % 3;
     for (int X = X0 - 4; X < X1; ++X) {
-      if (X > X0 - 4) ga_bar_sync<NT>(2 + ((X - 1) & 1));  // aux finished step X-1
       if (X >= X0 && jac) {
-      const double *stc0 = s.st[X & 3], *stc1 = s.st[(X - 1) & 3];  // cell columns X and X-1
+      const double *stc0 = s.st[xm3], *stc1 = s.st[xm3 == 0 ? 2 : xm3 - 1];  // cell columns X and X-1
       double *stg0 = s.stage[X & 1];
       double v00 = 0, v01 = 0, v10 = 0, v11 = 0, tu0 = 0, tu1 = 0, tt = 0;
         int nev = 0;  // cells summed into the current output (constant parts are added at the flush)
@@ -547,7 +538,7 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
         const int cx = X - (int)((info >> 4) & 1);
         uint4 v = {0, 0, 0, 0};
         if (cx >= 0 && cx < a.nx && (info & (1u << 18)))
-          v = GA_LDG(reinterpret_cast<const uint4 *>(a.ptab) + ((int64_t)s.cls[cx & 7][info & 15] * 81 + ((info >> 11) & 127)));
+          v = GA_LDG(reinterpret_cast<const uint4 *>(a.ptab) + ((int64_t)s.cls[cx & 3][info & 15] * 81 + ((info >> 11) & 127)));
         return v;
       };
       uint4 rec_nxt = load_rec(0);
@@ -620,9 +611,9 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
         }
       }
       ga_fence_async();  // staged entries -> visible to the TMA (async proxy) reads of the next step
+        xm3 = xm3 == 2 ? 0 : xm3 + 1;
       }
-      ga_bar_arrive<NT>(4 + (X & 1));  // matrix finished step X: lists of column X staged
+      ga_bar_step<NT>();
     }
-    ga_bar_sync<NT>(2 + ((X1 - 1) & 1));
   }
 }

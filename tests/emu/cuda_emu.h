@@ -42,25 +42,8 @@ static inline unsigned char *emu_smem() { return g_emu_smem; }
 static pthread_barrier_t g_emu_bar_all, g_emu_bar_warp[64];
 static double g_emu_xbuf[64][32];
 static inline void __syncthreads() { pthread_barrier_wait(&g_emu_bar_all); }
-// named barriers with arrive / sync semantics (bar.arrive does not block)
-struct EmuNamedBar { pthread_mutex_t mu; pthread_cond_t cv; int count; unsigned gen; };
-static EmuNamedBar g_emu_nb[16];
 template <int NT>
-static inline void ga_bar_arrive(int id) {
-  EmuNamedBar &b = g_emu_nb[id];
-  pthread_mutex_lock(&b.mu);
-  if (++b.count == NT) { b.count = 0; ++b.gen; pthread_cond_broadcast(&b.cv); }
-  pthread_mutex_unlock(&b.mu);
-}
-template <int NT>
-static inline void ga_bar_sync(int id) {
-  EmuNamedBar &b = g_emu_nb[id];
-  pthread_mutex_lock(&b.mu);
-  const unsigned g = b.gen;
-  if (++b.count == NT) { b.count = 0; ++b.gen; pthread_cond_broadcast(&b.cv); }
-  else while (b.gen == g) pthread_cond_wait(&b.cv, &b.mu);
-  pthread_mutex_unlock(&b.mu);
-}
+static inline void ga_bar_step() { pthread_barrier_wait(&g_emu_bar_all); }
 // full-warp butterfly shuffle: all 32 threads of the warp must call it
 static inline double ga_shfl_xor(double v, int mask) {
   const unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31;
@@ -123,7 +106,6 @@ static int emu_launch(void (*kernel)(Args), Args args, unsigned gx, unsigned gy,
     for (unsigned bx = 0; bx < gx; ++bx) {
       memset(g_emu_smem, 0x7F, smem_bytes);  // poison: huge doubles, huge positive ints (a stale dof id faults)
       pthread_barrier_init(&g_emu_bar_all, nullptr, nthreads);
-      for (int k = 0; k < 16; ++k) { pthread_mutex_init(&g_emu_nb[k].mu, nullptr); pthread_cond_init(&g_emu_nb[k].cv, nullptr); g_emu_nb[k].count = 0; g_emu_nb[k].gen = 0; }
       for (unsigned w = 0; w < nthreads / 32; ++w) pthread_barrier_init(&g_emu_bar_warp[w], nullptr, 32);
       for (unsigned t = 0; t < nthreads; ++t) {
         la[t].kernel = kernel; la[t].args = args; la[t].bidx.x = bx; la[t].bidx.y = by; la[t].t = t;

@@ -136,7 +136,7 @@ PARAMS = [
 ]
 CART_CASES = [
     ("1x1", 1, 1, cases.TURAN), ("2x3_wave", 2, 3, cases.WAVE), ("8x8_simple", 8, 8, cases.SIMPLE),
-    ("13x7_turan", 13, 7, cases.TURAN), ("5x19_turan", 5, 19, cases.TURAN), ("130x3_wave", 130, 3, cases.WAVE), ("259x2_turan", 259, 2, cases.TURAN),
+    ("13x7_turan", 13, 7, cases.TURAN), ("5x19_turan", 5, 19, cases.TURAN), ("130x3_wave", 130, 3, cases.WAVE), ("259x2_turan", 259, 2, cases.TURAN), ("515x1_simple", 515, 1, cases.SIMPLE),
 ]
 
 
