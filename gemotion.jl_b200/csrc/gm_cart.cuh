@@ -74,6 +74,10 @@ struct gm_cart {
   gm_params last_prm;
   bool tab_valid = false;
   int th = 8;  // cell rows per strip (template parameter of k_cart)
+  // kernel selection, read from the environment when the handle is created (A/B measurements and tests):
+  // GM_CART_KERNEL=sweep -> first-generation k_cart (gm_cart_kernel.cuh); default: k_gath (gm_gath_kernel.cuh)
+  bool use_sweep = false;
+  int gath_ng = 2;  // GM_GATH_NG: trios of matrix warps per CTA (1 or 2)
 };
 
 
@@ -214,6 +218,12 @@ static int gm_cart_create(gm_handle *h) {
   gm_cart *c = new (std::nothrow) gm_cart();
   if (!c) return GM_ERR_OOM;
   h->cart = c;
+  {
+    const char *e = getenv("GM_CART_KERNEL");
+    c->use_sweep = e && strcmp(e, "sweep") == 0;
+    e = getenv("GM_GATH_NG");
+    c->gath_ng = (e && atoi(e) == 1) ? 1 : 2;
+  }
   h->active_path = GM_PATH_CART;  // confirmed (or revoked) by gm_cart_after_pattern
   return GM_OK;
 }
@@ -366,11 +376,8 @@ static int gm_cart_run(gm_handle *h, const double *d_x, double *d_nz, double *d_
     ++*launches;
   }
   const bool csr = h->d.layout == GM_LAYOUT_CSR;
-  // GM_CART_KERNEL=sweep selects the first-generation kernel (k_cart) for A/B measurements
-  static const bool use_sweep = [] { const char *e = getenv("GM_CART_KERNEL"); return e && strcmp(e, "sweep") == 0; }();
-  static const int gath_ng = [] { const char *e = getenv("GM_GATH_NG"); return e ? atoi(e) : 2; }();
-  if (use_sweep) rc = gm_cart_launch<4>(h, a, csr, newt);
-  else rc = gath_ng == 1 ? gm_gath_launch<1>(h, a, csr, newt) : gm_gath_launch<2>(h, a, csr, newt);
+  if (c->use_sweep) rc = gm_cart_launch<4>(h, a, csr, newt);
+  else rc = c->gath_ng == 1 ? gm_gath_launch<1>(h, a, csr, newt) : gm_gath_launch<2>(h, a, csr, newt);
   if (rc) return rc;
   ++*launches;
   GM_CUDA(cudaGetLastError());

@@ -107,6 +107,7 @@ CART_CASES = [
     ("8x8_simple", 8, 8, cases.SIMPLE), ("13x7_turan", 13, 7, cases.TURAN), ("1x1", 1, 1, cases.TURAN),
     ("2x3_wave", 2, 3, cases.WAVE), ("20x19_turan", 20, 19, cases.TURAN), ("70x17_simple", 70, 17, cases.SIMPLE),
     ("130x9_wave", 130, 9, cases.WAVE), ("3x40_turan", 3, 40, cases.TURAN), ("65x24_turan", 65, 24, cases.TURAN),
+    ("300x5_simple", 300, 5, cases.SIMPLE),
 ]
 
 
@@ -120,6 +121,22 @@ def test_structured_path_matches_oracle(gm, gpu_lib, case, pi, layout):
     x = fe.splitmix_iterate(sp.n_total, 1234)
     info = _check(gm, sp, PARAMS[pi], layout, gm.capi.GM_PATH_CART, x)
     assert info["active_path"] == gm.capi.GM_PATH_CART
+
+
+@pytest.mark.parametrize("kernel", ["sweep", "gath_ng1"])
+@pytest.mark.parametrize("case", [CART_CASES[1], CART_CASES[6], CART_CASES[9]], ids=lambda c: c[0])
+@pytest.mark.parametrize("layout", ["csc", "csr"])
+def test_structured_path_other_kernels(gm, gpu_lib, monkeypatch, kernel, case, layout):
+    """The first-generation sweep kernel (GM_CART_KERNEL=sweep) and the one-trio configuration of k_gath stay green."""
+    if kernel == "sweep":
+        monkeypatch.setenv("GM_CART_KERNEL", "sweep")
+    else:
+        monkeypatch.setenv("GM_GATH_NG", "1")
+    _, nx, ny, bc = case
+    sp = cases.cart(nx, ny, bc=bc, domain=(0, 1.5, 0, 1))
+    x = fe.splitmix_iterate(sp.n_total, 1234)
+    for pi in (0, 1):
+        _check(gm, sp, PARAMS[pi], layout, gm.capi.GM_PATH_CART, x)
 
 
 def test_structured_equals_scatter_256(gm, gpu_lib):
