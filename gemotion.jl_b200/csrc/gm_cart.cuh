@@ -287,12 +287,10 @@ decided:
     CB(cudaMemcpy(c->ptab, pt.data(), pt.size(), cudaMemcpyHostToDevice));
     h->device_bytes += (int64_t)pt.size();
   }
-  if (c->use_sweep) {  // per-cell viscosity of the k_ct_visc pre-pass (k_gath evaluates it with its state)
-    CB(cudaMalloc(&c->visc, sizeof(double) * 8 * nc));
-    h->device_bytes += 64 * nc;
-  }
+  CB(cudaMalloc(&c->visc, sizeof(double) * 8 * nc));
   CB(cudaMalloc(&c->d_tab, sizeof(CartPairTab) * 81));
   CB(cudaMalloc(&c->d_cell, sizeof(CartCell)));
+  h->device_bytes += 64 * nc;
   // the per-cell rank table is no longer needed (the class table replaces it)
   cudaFree(h->rank);
   h->rank = nullptr;
@@ -373,7 +371,7 @@ static int gm_cart_run(gm_handle *h, const double *d_x, double *d_nz, double *d_
   a.tab = c->d_tab; a.cc = c->d_cell; a.x = d_x; a.nz = d_nz; a.b = d_b; a.flags = flags;
   a.Pr = p.Pr; a.RaPr = p.Ra * p.Pr; a.gx = p.gx; a.gy = p.gy; a.reg = p.reg; a.n = p.n; a.js = p.jac_scaling;
   const bool newt = p.n == 1.0;
-  if (!newt && c->use_sweep) {  // (k_gath evaluates the viscosity with the per-cell state)
+  if (!newt) {
     k_ct_visc<<<gm_blocks(h->ncells * 4, 256), 256, 0, h->stream>>>(h->ncells, h->gdofs, h->dvals, d_x, c->d_cell, p.reg, p.n, c->visc);
     ++*launches;
   }

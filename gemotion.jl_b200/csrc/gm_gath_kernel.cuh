@@ -155,6 +155,7 @@ struct GaSmem {
   double st[3][NR * GA_CS];          // state ring (cell column mod 3)
   double stage[2][QH * GA_QSTRIDE];  // staged lists of quad column X (X & 1)
   double val[4][NR][30];             // iterate values of cell column c (c & 3)
+  double visc[4][NR][4][2];
   long long lbase[4][QH][16];        // list bases / ends of quad column X (X & 3); 15 used
   long long lnext[4][QH][16];
   double ltk[3 * NG * 32];           // per matrix lane: TK of its node pair
@@ -239,7 +240,7 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
       ga_cp4(&s.gd[c & 7][rr][l], a.gdofs + ((int64_t)(Yc0 + rr) * a.nx + c) * 30 + l);
     }
   };
-  // (A2) iterate values and rank class of cell column c (its dof ids have landed)
+  // (A2) iterate values, viscosity, rank class of cell column c (its dof ids have landed)
   auto issue_val = [&](int c) {
     if (!col_ok(c)) return;
     for (int k = at_hi; k < NR * 30; k += NAT) {
@@ -252,6 +253,7 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
       const int rr = k >> 2, q = k & 3;
       if (!row_in_table(rr)) continue;
       const int64_t cell = (int64_t)(Yc0 + rr) * a.nx + c;
+      if (!NEWT) ga_cp16(&s.visc[c & 3][rr][q][0], a.visc + (cell * 4 + q) * 2);
       if (q == 0) ga_cp4(&s.cls[c & 3][rr], a.cls + cell);
     }
   };
@@ -273,13 +275,21 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
           u0 = fma(ph, ux, u0); G00 = fma(dx, ux, G00); G10 = fma(dy, ux, G10);
           u1 = fma(ph, uy, u1); G01 = fma(dx, uy, G01); G11 = fma(dy, uy, G11);
         }
+        const double D01 = 0.5 * (G01 + G10);
+        const double mu = NEWT ? 1.0 : s.visc[c & 3][rr][q][0];
+        const double wj = a.js * s.tw[q] * a.Pr, mup = wj * mu, sc = NEWT ? 0.0 : 2.0 * wj * s.visc[c & 3][rr][q][1];
+        const double s00 = sc * G00, s01 = sc * D01, s11 = sc * G11;
+        const double A0 = fma(s00, G00, 2.0 * mup), A1 = fma(s11, G11, 2.0 * mup), BM = fma(s01, D01, mup);
+        const double AA = s00 * G11, C1 = s00 * D01, C2 = s01 * G11;
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
           const double sx = (m & 1) ? -1.0 : 1.0, sy = (m & 2) ? -1.0 : 1.0, sxy = sx * sy;
           double *o = cs + m * GA_VS + (q ^ m) * GA_QS;
+          o[GS_A0] = A0; o[GS_A1] = A1; o[GS_BM] = BM; o[GS_AA] = AA; o[GS_C1] = sxy * C1; o[GS_C2] = sxy * C2;
           o[GS_G00] = G00; o[GS_G01] = sxy * G01; o[GS_G10] = sxy * G10; o[GS_G11] = G11;
           o[GS_U0] = sx * u0; o[GS_U1] = sy * u1;
         }
+        cs[q * GA_QS + GS_MUR] = mu;
       } else if (g == 1) {  // temperature
         double T = 0, d0 = 0, d1 = 0;
 #pragma unroll
@@ -293,35 +303,10 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
           o[GS_DT0] = d0; o[GS_DT1] = d1;
         }
         cs[4 * GA_QS + 2 * q + 1] = T;
-      } else {              // pressure; viscosity mu = gamma^((n-1)/2), kappa = 2 (n-1) gamma^((n-3)/2), gamma = reg + 2 D:D
-                            // (Solver.jl:113-120) and the six coefficients of the UU block
+      } else {              // pressure
         double p = 0;
 #pragma unroll
         for (int m = 0; m < 3; ++m) p += s.tpsi[q][m] * vv[18 + m];
-        double G00 = 0, G01 = 0, G10 = 0, G11 = 0;
-#pragma unroll
-        for (int i = 0; i < 9; ++i) {
-          const double dx = s.tdx[q][i], dy = s.tdy[q][i], ux = vv[i], uy = vv[9 + i];
-          G00 = fma(dx, ux, G00); G10 = fma(dy, ux, G10); G01 = fma(dx, uy, G01); G11 = fma(dy, uy, G11);
-        }
-        const double D01 = 0.5 * (G01 + G10);
-        double mu = 1.0, kap = 0.0;
-        if (!NEWT) {
-          const double gam = a.reg + 2.0 * (G00 * G00 + 2.0 * D01 * D01 + G11 * G11);
-          mu = pow(gam, 0.5 * (a.n - 1.0));
-          kap = 0.5 * (a.n - 1.0) * pow(gam, 0.5 * (a.n - 3.0)) * 4.0;
-        }
-        const double wj = a.js * s.tw[q] * a.Pr, mup = wj * mu, sc = 2.0 * wj * kap;
-        const double s00 = sc * G00, s01 = sc * D01, s11 = sc * G11;
-        const double A0 = fma(s00, G00, 2.0 * mup), A1 = fma(s11, G11, 2.0 * mup), BM = fma(s01, D01, mup);
-        const double AA = s00 * G11, C1 = s00 * D01, C2 = s01 * G11;
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          const double sxy = (m == 1 || m == 2) ? -1.0 : 1.0;
-          double *o = cs + m * GA_VS + (q ^ m) * GA_QS;
-          o[GS_A0] = A0; o[GS_A1] = A1; o[GS_BM] = BM; o[GS_AA] = AA; o[GS_C1] = sxy * C1; o[GS_C2] = sxy * C2;
-        }
-        cs[q * GA_QS + GS_MUR] = mu;
         cs[4 * GA_QS + 2 * q] = p;
       }
     }

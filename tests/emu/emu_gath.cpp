@@ -5,6 +5,27 @@
 #include "../../gemotion.jl_b200/csrc/gm_cart_tables.h"
 #include "../../gemotion.jl_b200/csrc/gm_gath_kernel.cuh"
 
+// viscosity pre-pass, same arithmetic as k_ct_visc (gm_cart.cuh)
+static void emu_visc(int64_t ncells, const int32_t *g, const double *dvals, const double *x, const CartCell *cc, double reg,
+                     double n, double *visc) {
+  for (int64_t t = 0; t < ncells * 4; ++t) {
+    const int64_t c = t >> 2;
+    const int q = (int)(t & 3);
+    double G00 = 0, G01 = 0, G10 = 0, G11 = 0;
+    for (int i = 0; i < 9; ++i) {
+      const int32_t d0 = g[c * 30 + i], d1 = g[c * 30 + 9 + i];
+      const double ux = d0 > 0 ? x[d0 - 1] : dvals[-d0 - 1];
+      const double uy = d1 > 0 ? x[d1 - 1] : dvals[-d1 - 1];
+      const double dx = cc->sdx[q][i], dy = cc->sdy[q][i];
+      G00 += dx * ux; G01 += dx * uy; G10 += dy * ux; G11 += dy * uy;
+    }
+    const double D01 = 0.5 * (G01 + G10);
+    const double gam = reg + 2.0 * (G00 * G00 + 2.0 * D01 * D01 + G11 * G11);
+    visc[t * 2] = pow(gam, 0.5 * (n - 1.0));
+    visc[t * 2 + 1] = 0.5 * (n - 1.0) * pow(gam, 0.5 * (n - 3.0)) * 4.0;
+  }
+}
+
 template <int NG>
 static int run(CartArgs a, bool csr, bool newt) {
   const unsigned nt = (3 * NG + GA_NAUX) * 32;
@@ -23,10 +44,13 @@ extern "C" int emu_gath_run(int nx, int ny, int row_begin, int row_end, const in
   gm_cart_fill_tables(w, phi, dphi, psi, hx, hy, prm[0], prm[1], prm[4], prm[5], prm[6], tab, &cell);
   std::vector<uint8_t> ptab((size_t)nclass * 81 * 16);
   gm_cart_pair_ranks(nclass, ctab, ptab.data());
+  const int64_t ncells = (int64_t)nx * ny;
+  std::vector<double> visc((size_t)ncells * 8, 0.0);
   const bool newt = prm[2] == 1.0;
+  if (!newt) emu_visc(ncells, gdofs, dvals, x, &cell, prm[3], prm[2], visc.data());
   CartArgs a;
   a.nx = nx; a.ny = ny; a.row_begin = row_begin; a.row_end = row_end;
-  a.gdofs = gdofs; a.dvals = dvals; a.ptr = ptr; a.cls = cls; a.ctab = ctab; a.ptab = ptab.data(); a.visc = nullptr;
+  a.gdofs = gdofs; a.dvals = dvals; a.ptr = ptr; a.cls = cls; a.ctab = ctab; a.ptab = ptab.data(); a.visc = visc.data();
   a.tab = tab; a.cc = &cell; a.x = x; a.nz = nz; a.b = b; a.flags = flags;
   a.Pr = prm[0]; a.RaPr = prm[1] * prm[0]; a.gx = prm[4]; a.gy = prm[5]; a.reg = prm[3]; a.n = prm[2]; a.js = prm[6];
   g_emu_bulk_misaligned = 0;
