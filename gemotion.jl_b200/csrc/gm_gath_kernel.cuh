@@ -284,10 +284,10 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
           const double sx = (m & 1) ? -1.0 : 1.0, sy = (m & 2) ? -1.0 : 1.0, sxy = sx * sy;
-          double *o = cs + m * GA_VS + (q ^ m) * GA_QS;
-          o[GS_A0] = A0; o[GS_A1] = A1; o[GS_BM] = BM; o[GS_AA] = AA; o[GS_C1] = sxy * C1; o[GS_C2] = sxy * C2;
-          o[GS_G00] = G00; o[GS_G01] = sxy * G01; o[GS_G10] = sxy * G10; o[GS_G11] = G11;
-          o[GS_U0] = sx * u0; o[GS_U1] = sy * u1;
+          double2 *o = reinterpret_cast<double2 *>(cs + m * GA_VS + (q ^ m) * GA_QS);  // 16-byte stores: pairs as the lanes load them
+          o[GS_A0 / 2] = make_double2(A0, A1); o[GS_BM / 2] = make_double2(BM, AA); o[GS_C1 / 2] = make_double2(sxy * C1, sxy * C2);
+          o[GS_G00 / 2] = make_double2(G00, G11); o[GS_G01 / 2] = make_double2(sxy * G01, sxy * G10);
+          o[GS_U0 / 2] = make_double2(sx * u0, sy * u1);
         }
         cs[q * GA_QS + GS_MUR] = mu;
       } else if (g == 1) {  // temperature
@@ -299,8 +299,7 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
         }
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
-          double *o = cs + m * GA_VS + (q ^ m) * GA_QS;
-          o[GS_DT0] = d0; o[GS_DT1] = d1;
+          reinterpret_cast<double2 *>(cs + m * GA_VS + (q ^ m) * GA_QS)[GS_DT0 / 2] = make_double2(d0, d1);
         }
         cs[4 * GA_QS + 2 * q + 1] = T;
       } else {              // pressure

@@ -29,6 +29,7 @@ struct emu_dim3 { unsigned x = 1, y = 1, z = 1; };
 static thread_local emu_dim3 threadIdx, blockIdx;
 static emu_dim3 blockDim, gridDim;
 struct double2 { double x, y; };
+static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 struct uint4 { uint32_t x, y, z, w; };
 using std::min;
 using std::max;
