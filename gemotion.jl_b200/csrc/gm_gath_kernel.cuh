@@ -231,24 +231,38 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
   static_assert(NAT == 192, "the aux task split below assumes six aux warps");
   const int at_hi = NAT - 1 - at;                              // item order for the two-pass loops
   const int at_o = at < 64 ? at : (at >= 128 ? at - 64 : -1);  // 0..127 on w0, w1, w4, w5
+  // (A1/A2) every aux thread owns up to two fixed (state row, local dof) items of a cell column: the row / dof
+  //         split and the row part of the addresses are loop invariant, a column only adds its offset
+  static_assert(NR * 30 <= 2 * NAT, "two load items per aux thread");
+  int li_off[2];          // item index rr*30 + l (-1: none)
+  int64_t li_goff[2];     // offset of the item in gdofs for column 0
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int k = at_hi + j * NAT, rr = k / 30;
+    const bool ok = k < NR * 30 && row_in_table(rr);
+    li_off[j] = ok ? k : -1;
+    li_goff[j] = ok ? (int64_t)(Yc0 + rr) * a.nx * 30 + (k - rr * 30) : 0;
+  }
   // (A1) dof ids of cell column c
   auto issue_gd = [&](int c) {
     if (!col_ok(c)) return;
-    for (int k = at_hi; k < NR * 30; k += NAT) {
-      const int rr = k / 30, l = k - rr * 30;
-      if (!row_in_table(rr)) continue;
-      ga_cp4(&s.gd[c & 7][rr][l], a.gdofs + ((int64_t)(Yc0 + rr) * a.nx + c) * 30 + l);
-    }
+    int32_t *dst = &s.gd[c & 7][0][0];
+    const int32_t *src = a.gdofs + (int64_t)c * 30;
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      if (li_off[j] >= 0) ga_cp4(dst + li_off[j], src + li_goff[j]);
   };
   // (A2) iterate values, viscosity, rank class of cell column c (its dof ids have landed)
   auto issue_val = [&](int c) {
     if (!col_ok(c)) return;
-    for (int k = at_hi; k < NR * 30; k += NAT) {
-      const int rr = k / 30, l = k - rr * 30;
-      if (!row_in_table(rr)) continue;
-      const int32_t d = s.gd[c & 7][rr][l];
-      ga_cp8(&s.val[c & 3][rr][l], d > 0 ? a.x + (d - 1) : a.dvals + (-d - 1));
-    }
+    const int32_t *gdc = &s.gd[c & 7][0][0];
+    double *dst = &s.val[c & 3][0][0];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      if (li_off[j] >= 0) {
+        const int32_t d = gdc[li_off[j]];
+        ga_cp8(dst + li_off[j], d > 0 ? a.x + (d - 1) : a.dvals + (-d - 1));
+      }
     for (int k = at; k < NR * 4; k += NAT) {
       const int rr = k >> 2, q = k & 3;
       if (!row_in_table(rr)) continue;
@@ -377,6 +391,9 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
       pe_val = (CSR ? -1.0 : 1.0) * s.UP[ud][p];
     }
   }
+  // rank of this thread's entry type in one (interior) class, kept in a register: the table is only read for other classes
+  const int pe_cls0 = pe_on ? a.cls[(int64_t)min(max(Yc0 + 3, 0), a.ny - 1) * a.nx + min(X0 + 3, a.nx - 1)] : 0;
+  const int pe_rk0 = pe_on ? (int)GA_LDG(a.ctab + (int64_t)pe_cls0 * 900 + pe_rk) : 0xFF;
   auto p_entries = [&](int X) {
     if (!pe_on) return;
     const int cx = X - pe_dx;
@@ -389,7 +406,8 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
       const int rr = rowq + 1 - pe_dy;
       own[rowq] = row_owned(rr);
       const bool ok = rowq < nqr && row_in_table(rr) && (own[rowq] || !pe_plist);
-      rk[rowq] = ok ? (int)GA_LDG(a.ctab + (int64_t)s.cls[cx & 3][ok ? rr : 0] * 900 + pe_rk) : 0xFF;
+      const int cl = ok ? s.cls[cx & 3][rr] : pe_cls0;
+      rk[rowq] = !ok ? 0xFF : (cl == pe_cls0 ? pe_rk0 : (int)GA_LDG(a.ctab + (int64_t)cl * 900 + pe_rk));
     }
 #pragma unroll
     for (int rowq = 0; rowq < QH; ++rowq) {

@@ -54,7 +54,7 @@ extern "C" int emu_gath_run(int nx, int ny, int row_begin, int row_end, const in
   a.tab = tab; a.cc = &cell; a.x = x; a.nz = nz; a.b = b; a.flags = flags;
   a.Pr = prm[0]; a.RaPr = prm[1] * prm[0]; a.gx = prm[4]; a.gy = prm[5]; a.reg = prm[3]; a.n = prm[2]; a.js = prm[6];
   g_emu_bulk_misaligned = 0;
-  int rc = ng == 1 ? run<1>(a, csr != 0, newt) : (ng == 2 ? run<2>(a, csr != 0, newt) : run<3>(a, csr != 0, newt));
+  int rc = ng == 1 ? run<1>(a, csr != 0, newt) : run<2>(a, csr != 0, newt);  // the configurations the library instantiates
   if (diag) diag[0] = g_emu_bulk_misaligned;
   return rc;
 }
