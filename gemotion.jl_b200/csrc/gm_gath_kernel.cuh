@@ -271,27 +271,21 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
       if (q == 0) ga_cp4(&s.cls[c & 3][rr], a.cls + cell);
     }
   };
-  // (A3) state of cell column c: fields at the quadrature points, four mirror variants.  Every aux thread owns ONE
-  //      item (kind g: velocity / temperature / pressure, state row, point): the shape tables of its point live in registers.
-  static_assert(NAT == 3 * 64 && NR <= 16, "one state item per aux thread");
-  const int st_k = at < 64 ? at + 64 : (at < 128 ? at - 64 : at);  // g-major: velocity items (0..63) on w2, w3
-  const int st_g = st_k >> 6, st_rr = (st_k & 63) >> 2, st_q = st_k & 3;
-  const bool st_on = st_rr < NR && row_owned(st_rr);
-  double st_phi[9], st_dx[9], st_dy[9];
-#pragma unroll
-  for (int i = 0; i < 9; ++i) { st_phi[i] = s.tphi[st_q][i]; st_dx[i] = s.tdx[st_q][i]; st_dy[i] = s.tdy[st_q][i]; }
+  // (A3) state of cell column c: fields at the quadrature points, four mirror variants
   auto state = [&](int c) {
     if (!col_ok(c)) return;
     double *sc0 = s.st[c % 3];
-    if (st_on) {
-      const int g = st_g, rr = st_rr, q = st_q;
+    for (int k0 = at; k0 < 3 * 64; k0 += NAT) {  // g-major item order: a warp runs one kind of item;
+      const int k = k0 < 64 ? k0 + 64 : (k0 < 128 ? k0 - 64 : k0);  // velocity items (0..63) on w2, w3
+      const int g = k >> 6, e = k & 63, rr = e >> 2, q = e & 3;
+      if (rr >= NR || !row_owned(rr)) continue;
       double *cs = sc0 + rr * GA_CS;
       const double *vv = &s.val[c & 3][rr][0];
       if (g == 0) {         // velocity
         double u0 = 0, u1 = 0, G00 = 0, G01 = 0, G10 = 0, G11 = 0;
 #pragma unroll
         for (int i = 0; i < 9; ++i) {
-          const double ph = st_phi[i], dx = st_dx[i], dy = st_dy[i], ux = vv[i], uy = vv[9 + i];
+          const double ph = s.tphi[q][i], dx = s.tdx[q][i], dy = s.tdy[q][i], ux = vv[i], uy = vv[9 + i];
           u0 = fma(ph, ux, u0); G00 = fma(dx, ux, G00); G10 = fma(dy, ux, G10);
           u1 = fma(ph, uy, u1); G01 = fma(dx, uy, G01); G11 = fma(dy, uy, G11);
         }
@@ -315,7 +309,7 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
 #pragma unroll
         for (int i = 0; i < 9; ++i) {
           const double tv = vv[21 + i];
-          T = fma(st_phi[i], tv, T); d0 = fma(st_dx[i], tv, d0); d1 = fma(st_dy[i], tv, d1);
+          T = fma(s.tphi[q][i], tv, T); d0 = fma(s.tdx[q][i], tv, d0); d1 = fma(s.tdy[q][i], tv, d1);
         }
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
@@ -424,27 +418,21 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
   };
   // (A6) residual of the dofs of quad column X: lane quartet = the (up to) four cells of one node; partial sums
   //      are combined by two butterfly shuffles, lane 0 of the quartet stores the three dofs of the node
-  static_assert(QH * 16 + 64 <= NAT, "one residual item per thread of w2..w5");
-  const int rs_k = at - 64;  // (w2..w5; negative on w0, w1: no item)
-  const int rs_rowq = rs_k < 0 ? QH : (rs_k >> 4), rs_An = (rs_k >> 2) & 3, rs_sv = rs_k & 3;
-  const int rs_m = ga_var(rs_An, rs_sv < ga_nvar(rs_An) ? rs_sv : 0), rs_rr = rs_rowq + 1 - (rs_m >> 1), rs_nd = ga_anode(rs_An, rs_m);
-  const bool rs_on = rs_rowq < nqr && rs_sv < ga_nvar(rs_An) && row_owned(rs_rr);
-  double rs_ph[4], rs_gx[4], rs_gy[4];  // shape function of the item's node at the four points
-#pragma unroll
-  for (int q = 0; q < 4; ++q) { rs_ph[q] = s.tphi[q][rs_nd]; rs_gx[q] = s.tdx[q][rs_nd]; rs_gy[q] = s.tdy[q][rs_nd]; }
   auto residual = [&](int X) {
-    {
-      const int rowq = rs_rowq, An = rs_An, sv = rs_sv;
+    for (int k0 = 0; k0 < QH * 16; k0 += NAT) {  // (NAT is a multiple of 32: whole warps enter together)
+      const int k = k0 + at - 64;  // (w2..w5; negative on w0, w1: no item)
+      const int rowq = k < 0 ? QH : (k >> 4), An = (k >> 2) & 3, sv = k & 3;
       double r0 = 0, r1 = 0, r2 = 0;
-      {
-        const int cx = X - (rs_m & 1);
-        if (rs_on && col_ok(cx)) {
-          const double *cs = s.st[cx % 3] + rs_rr * GA_CS;
+      if (rowq < nqr && sv < ga_nvar(An)) {
+        const int m = ga_var(An, sv), cx = X - (m & 1), rr = rowq + 1 - (m >> 1);
+        if (col_ok(cx) && row_owned(rr)) {
+          const int nd = ga_anode(An, m);
+          const double *cs = s.st[cx % 3] + rr * GA_CS;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const double *u = cs + q * GA_QS;
-            const double w = s.tw[q], gx_ = rs_gx[q], gy_ = rs_gy[q];
-            const double ph = w * rs_ph[q], dx = w * gx_, dy = w * gy_;
+            const double w = s.tw[q], gx_ = s.tdx[q][nd], gy_ = s.tdy[q][nd];
+            const double ph = w * s.tphi[q][nd], dx = w * gx_, dy = w * gy_;
             const double u0 = u[GS_U0], u1 = u[GS_U1], G00 = u[GS_G00], G01 = u[GS_G01], G10 = u[GS_G10], G11 = u[GS_G11];
             const double D01 = 0.5 * (G01 + G10), pq = cs[4 * GA_QS + 2 * q], Tq = cs[4 * GA_QS + 2 * q + 1];
             const double m2 = 2.0 * a.Pr * w * u[GS_MUR], bu = a.RaPr * Tq;
