@@ -12,18 +12,23 @@
 //    left of / below a node equal those of the mirrored pair of the cell right of / above it, with the
 //    quadrature points permuted and sign flips on odd x/y derivative counts.  The flips are moved into the
 //    per-cell STATE, of which four variants (I, X, Y, XY) are kept in shared memory: variant m stores at
-//    slot q the fields of the actual point q^m, with G01, G10, D01 multiplied by sx*sy and (u0,u1) by
-//    (sx,sy).  A lane therefore keeps ONE set of 43 table values in registers and evaluates any of its
-//    cells with the same instruction stream; only v01, v10 need the sign sx*sy when they are merged.
+//    slot q the fields of the actual point q^m, with G01, G10 and the coefficients C1, C2 multiplied by
+//    sx*sy and (u0,u1) by (sx,sy).  A lane therefore keeps ONE set of 28 table values in registers and
+//    evaluates any of its cells with the same instruction stream; only v01, v10 need the sign sx*sy when
+//    they are merged.
+//  * Six coefficients: the UU block is sum_q sum_kl C^ab_kl(q) (d_k phi_i d_l phi_j)(q) and the C^ab_kl reduce to
+//    six numbers per quadrature point (see the state record below), computed once per cell with the state.
 //  * Work unit: a "quad" = the four nodes (V vertex, H bottom-edge, E left-edge, C centre) at the lower left
 //    of a cell.  Four vertically adjacent quads = 64 output node pairs x 9 entries = 81 cell-pair
 //    evaluations per cell = 81 lanes x 4 rounds: V lanes (36) evaluate their 4 cells, E / H lanes (18 + 18)
 //    two quads x two cells, C lanes (9) four quads x one cell.  A trio of warps (27 lanes each) runs 4
 //    identical rounds per column; consecutive rounds that hit the same output are merged before the store.
-//  * CTA = NG trios + 2 aux warps, sweeping a strip of 4*NG quad rows column by column.  Aux warps: state
-//    of column X+1 (fields at the quadrature points, four variants), the constant P-block entries, the
-//    residual (written straight to b), list bases of column X+1 (cp.async), TMA write-out of column X-1.
-//    One CTA barrier per column.
+//  * CTA = NG trios + GA_NAUX aux warps (2 + 6 = 12 warps at 168 registers, 1 CTA/SM), sweeping a strip of
+//    4*NG quad rows column by column in two role-specific loops that meet at one named barrier per column.
+//    Aux warps: dof ids / iterate values / rank classes of the coming columns and list bases of column X+1
+//    (cp.async), state of column X+1 (four variants), the constant P-block entries, the residual (written
+//    straight to b), TMA write-out of column X-1.  Measurements and the experiments that did not help are in
+//    DESIGN.md section 4.
 //
 // The file compiles for the device (nvcc, sm_100a) and -- with GM_EMU -- as host C++ under
 // tests/emu/cuda_emu.h, which runs every CUDA thread as a pthread; that build exists only so that the
