@@ -341,17 +341,23 @@ static int gm_cart_launch(gm_handle *h, const CartArgs &a, bool csr, bool newt) 
 }
 
 // ---- k_gath (gm_gath_kernel.cuh): NG trios of matrix warps + GA_NAUX aux warps, one CTA per SM
-template <int NG, bool CSR, bool NEWT>
-static int gm_gath_launch1(gm_handle *h, const CartArgs &a) {
+template <int NG, bool CSR, bool NEWT, int XCH>
+static int gm_gath_launch2(gm_handle *h, const CartArgs &a, int nstrips) {
   static bool attr_set = false;
   const size_t sm = sizeof(GaSmem<NG>);
   if (!attr_set) {
-    GM_CUDA(cudaFuncSetAttribute(k_gath<NG, CSR, NEWT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    GM_CUDA(cudaFuncSetAttribute(k_gath<NG, CSR, NEWT, XCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     attr_set = true;
   }
-  dim3 grid((a.nx + 1 + GA_XCH - 1) / GA_XCH, (a.row_end - a.row_begin + 1 + 4 * NG - 1) / (4 * NG));
-  k_gath<NG, CSR, NEWT><<<grid, (3 * NG + GA_NAUX) * 32, sm, h->stream>>>(a);
+  dim3 grid((a.nx + 1 + XCH - 1) / XCH, nstrips);
+  k_gath<NG, CSR, NEWT, XCH><<<grid, (3 * NG + GA_NAUX) * 32, sm, h->stream>>>(a);
   return GM_OK;
+}
+template <int NG, bool CSR, bool NEWT>
+static int gm_gath_launch1(gm_handle *h, const CartArgs &a) {
+  const int nstrips = (a.row_end - a.row_begin + 1 + 4 * NG - 1) / (4 * NG);
+  return gm_gath_chunk(a.nx, nstrips, h->num_sms) == 128 ? gm_gath_launch2<NG, CSR, NEWT, 128>(h, a, nstrips)
+                                                         : gm_gath_launch2<NG, CSR, NEWT, 256>(h, a, nstrips);
 }
 template <int NG>
 static int gm_gath_launch(gm_handle *h, const CartArgs &a, bool csr, bool newt) {

@@ -82,6 +82,13 @@ static inline void gm_cart_fill_tables(const double *rw, const double *rphi, con
     }
 }
 
+// x-chunk length of k_gath (a template parameter: 256 or 128 quad columns).  Long chunks amortise the 4-step
+// pipeline warm-up (1.6 % at 256), but a rank of a multi-GPU run has few strips: the short chunk is taken when the
+// long one would leave fewer than ~12 waves of CTAs (one CTA per SM), so that the last, partially filled wave stays small.
+static inline int gm_gath_chunk(int nx, int nstrips, int nsm) {
+  return (long long)((nx + 1 + 255) / 256) * nstrips < 12LL * nsm ? 128 : 256;
+}
+
 // Pair-major copy of the class tables for k_gath: record [class][major node M][minor node m] holds the 9
 // ranks (list k of M) x (dof l of m) at byte k*3+l (bytes 9..15 unused), so a lane fetches them with one
 // 16-byte load.  ctab is [nclass][900] = rank[minor dof][major dof].  Entries without a position

@@ -35,7 +35,6 @@
 // index logic can be checked against the oracle without a GPU (tests/test_gath_emu.py).
 #pragma once
 
-#define GA_XCH 256                 // quad columns per x-chunk
 #define GA_NAUX 6                  // aux warps
 #define GA_MAXREG 168               // 65536 / (12 warps * 32): warps are allocated in fours
 #define GA_QS 16                   // doubles per (variant, point) state record
@@ -174,7 +173,7 @@ struct GaSmem {
   uint8_t pu[54][4];                 // (A, m, a, p) of the 54 P-row entries of a quad's U lists
 };
 
-template <int NG, bool CSR, bool NEWT>
+template <int NG, bool CSR, bool NEWT, int XCH>
 __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
   using S = GaSmem<NG>;
   constexpr int QH = S::QH, NR = S::NR;
@@ -191,7 +190,7 @@ __global__ void __maxnreg__(GA_MAXREG) k_gath(CartArgs a) {
   const int Yq0 = a.row_begin + (int)blockIdx.y * QH;     // first quad row of the strip
   const int nqr = min(QH, a.row_end + 1 - Yq0);           // quad rows Yq0 .. Yq0+nqr-1 (row_end = the top mesh line)
   const int Yc0 = Yq0 - 1;                                // cell row of state row 0
-  const int X0 = (int)blockIdx.x * GA_XCH, X1 = min(a.nx + 1, X0 + GA_XCH);
+  const int X0 = (int)blockIdx.x * XCH, X1 = min(a.nx + 1, X0 + XCH);  // quad columns of this x-chunk
   const bool jac = (a.flags & GM_JACOBIAN) != 0, res = (a.flags & GM_RESIDUAL) != 0;
   const CartCell &cc = *a.cc;
 

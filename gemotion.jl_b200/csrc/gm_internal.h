@@ -32,6 +32,7 @@ struct GmConst {
 struct gm_handle {
   gm_desc d;  // scalars only; every pointer member is nulled after gm_create
   int dev = 0;
+  int num_sms = 148;  // multiprocessors of the device (grid sizing)
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   int ld = 0, nn = 0, nq = 0, nv = 0;

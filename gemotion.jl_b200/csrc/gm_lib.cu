@@ -160,6 +160,10 @@ extern "C" int gm_create(const gm_desc *d, gm_handle **out) {
 #define TRY(x) do { rc = (x); if (rc != GM_OK) return fail(rc); } while (0)
 #define TRYC(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { gm_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); return fail(e__ == cudaErrorMemoryAllocation ? GM_ERR_OOM : GM_ERR_CUDA); } } while (0)
   TRYC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  {
+    int nsm = 0;
+    if (cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, d->device) == cudaSuccess && nsm > 0) h->num_sms = nsm;
+  }
   h->own_stream = true;
   for (int k = 0; k < 4; ++k) TRYC(cudaEventCreate(&h->ev[k]));
   // constants

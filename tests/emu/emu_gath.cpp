@@ -26,19 +26,19 @@ static void emu_visc(int64_t ncells, const int32_t *g, const double *dvals, cons
   }
 }
 
-template <int NG>
+template <int NG, int XCH>
 static int run(CartArgs a, bool csr, bool newt) {
   const unsigned nt = (3 * NG + GA_NAUX) * 32;
-  const unsigned gx = (a.nx + 1 + GA_XCH - 1) / GA_XCH, gy = (a.row_end - a.row_begin + 1 + 4 * NG - 1) / (4 * NG);
+  const unsigned gx = (a.nx + 1 + XCH - 1) / XCH, gy = (a.row_end - a.row_begin + 1 + 4 * NG - 1) / (4 * NG);
   const size_t sm = sizeof(GaSmem<NG>);
-  if (csr) return newt ? emu_launch(k_gath<NG, true, true>, a, gx, gy, nt, GA_NAUX * 32, sm) : emu_launch(k_gath<NG, true, false>, a, gx, gy, nt, GA_NAUX * 32, sm);
-  return newt ? emu_launch(k_gath<NG, false, true>, a, gx, gy, nt, GA_NAUX * 32, sm) : emu_launch(k_gath<NG, false, false>, a, gx, gy, nt, GA_NAUX * 32, sm);
+  if (csr) return newt ? emu_launch(k_gath<NG, true, true, XCH>, a, gx, gy, nt, GA_NAUX * 32, sm) : emu_launch(k_gath<NG, true, false, XCH>, a, gx, gy, nt, GA_NAUX * 32, sm);
+  return newt ? emu_launch(k_gath<NG, false, true, XCH>, a, gx, gy, nt, GA_NAUX * 32, sm) : emu_launch(k_gath<NG, false, false, XCH>, a, gx, gy, nt, GA_NAUX * 32, sm);
 }
 
 extern "C" int emu_gath_run(int nx, int ny, int row_begin, int row_end, const int32_t *gdofs, const double *dvals,
                             const int64_t *ptr, const int32_t *cls, int nclass, const uint8_t *ctab, const double *x, double *nz,
                             double *b, unsigned flags, int csr, const double *prm /*Pr Ra n reg gx gy js*/, double hx, double hy,
-                            const double *w, const double *phi, const double *dphi, const double *psi, int ng, int64_t *diag) {
+                            const double *w, const double *phi, const double *dphi, const double *psi, int ng, int xch, int64_t *diag) {
   static CartPairTab tab[81];
   static CartCell cell;
   gm_cart_fill_tables(w, phi, dphi, psi, hx, hy, prm[0], prm[1], prm[4], prm[5], prm[6], tab, &cell);
@@ -54,7 +54,9 @@ extern "C" int emu_gath_run(int nx, int ny, int row_begin, int row_end, const in
   a.tab = tab; a.cc = &cell; a.x = x; a.nz = nz; a.b = b; a.flags = flags;
   a.Pr = prm[0]; a.RaPr = prm[1] * prm[0]; a.gx = prm[4]; a.gy = prm[5]; a.reg = prm[3]; a.n = prm[2]; a.js = prm[6];
   g_emu_bulk_misaligned = 0;
-  int rc = ng == 1 ? run<1>(a, csr != 0, newt) : run<2>(a, csr != 0, newt);  // the configurations the library instantiates
+  // the configurations the library instantiates (x-chunks of 256 / 128 columns), plus 32-column chunks to exercise chunk seams on small meshes
+  int rc = ng == 1 ? (xch == 256 ? run<1, 256>(a, csr != 0, newt) : (xch == 128 ? run<1, 128>(a, csr != 0, newt) : run<1, 32>(a, csr != 0, newt)))
+                   : (xch == 256 ? run<2, 256>(a, csr != 0, newt) : (xch == 128 ? run<2, 128>(a, csr != 0, newt) : run<2, 32>(a, csr != 0, newt)));
   if (diag) diag[0] = g_emu_bulk_misaligned;
   return rc;
 }

@@ -93,7 +93,7 @@ def local_pattern(g, n):
     return ptr, idx
 
 
-def run_emu(emu, sp, prm, layout, x, rows=None, ng=2, flags=3):
+def run_emu(emu, sp, prm, layout, x, rows=None, ng=2, flags=3, xch=256):
     m = sp.model
     nx, ny_glob = m.partition
     g, dv = global_dofs(sp)
@@ -123,7 +123,7 @@ def run_emu(emu, sp, prm, layout, x, rows=None, ng=2, flags=3):
     rc = emu.emu_gath_run(C.c_int(nx), C.c_int(ny), C.c_int(rb), C.c_int(re), _p(g), _p(dv), _p(ptr), _p(cls),
                           C.c_int(ctab.shape[0]), _p(ctab), _p(xx), _p(nz), _p(b), C.c_uint(flags),
                           C.c_int(1 if layout == "csr" else 0), _p(pv), C.c_double(m.h[0]), C.c_double(m.h[1]),
-                          _p(w), _p(phi), _p(dphi), _p(psi), C.c_int(ng), _p(diag))
+                          _p(w), _p(phi), _p(dphi), _p(psi), C.c_int(ng), C.c_int(xch), _p(diag))
     assert rc == 0
     assert diag[0] == 0, "misaligned TMA bulk copy"
     return orc, ptr, idx, nz, b, g
@@ -147,7 +147,7 @@ def test_gather_kernel_logic_matches_oracle(emu, case, pi, layout):
     _, nx, ny, bc = case
     sp = cases.cart(nx, ny, bc=bc, domain=(0, 1.5, 0, 1))
     x = fe.splitmix_iterate(sp.n_total, 1234)
-    orc, ptr, idx, nz, b, _ = run_emu(emu, sp, PARAMS[pi], layout, x, ng=1 + (pi % 2))
+    orc, ptr, idx, nz, b, _ = run_emu(emu, sp, PARAMS[pi], layout, x, ng=1 + (pi % 2), xch=(256, 128, 32)[pi])
     onz, ob = orc.assemble(x, layout)
     assert not np.isnan(nz).any() and not np.isnan(b).any(), "every list position / residual entry must be written"
     assert cases.block_scaled_err(nz, onz, cases.nz_blocks(sp, ptr, idx)) <= TOL
