@@ -102,6 +102,7 @@ def cpu_pass(N, prm, passes, threads=None):
     from _pkg import gm
     if threads:
         os.environ["OMP_NUM_THREADS"] = str(threads)
+        Oracle.set_num_threads(threads)  # (the library may already be loaded with torchrun's OMP_NUM_THREADS=1)
     sp = build_problem(N)
     orc = Oracle(sp, **prm)
     x = gm.fe.splitmix_iterate(sp.n_total, 1234)
@@ -159,6 +160,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--force-e2e", action="store_true")
+    ap.add_argument("--no-verify", action="store_true", help="skip the sampled row-oracle check (outside the timed region)")
+    ap.add_argument("--verify-rows", type=int, default=2000, help="random major dofs checked besides the structural ones")
     args = ap.parse_args()
     if args.mesh == 0:
         # config 5 of BASELINE.json: 4096^2, n=1.4 -- the mesh the metric / target is quoted on; it fits one B200
@@ -255,6 +258,57 @@ def main():
             dist.all_reduce(t)
         chk_owned = float(t.item())
 
+    # ---- one synchronous step: the NCCL interface-row sum is timed by its own events (gm_times.exchange_ms)
+    h.assemble_device(d_x.data_ptr(), d_nz.data_ptr(), d_b.data_ptr(), flags, sync=True)
+    timing_sync = h.timing()
+
+    # ---- sampled row oracle (outside the timed region): the kernel that was just timed, at this size, through real NCCL
+    verify = None
+    if not args.no_verify:
+        import rowcheck
+        from oracle.oracle import Oracle
+        t0 = time.perf_counter()
+        rows = rowcheck.sample_rows(sp, nrandom=args.verify_rows)
+        orc = Oracle(sp, **prm)
+        verify = rowcheck.check_rows(sp, h, orc, x_host, d_nz.data_ptr(), d_b.data_ptr(), args.layout, rows)
+        del orc
+        if world > 1:
+            bad = torch.tensor([0 if verify["pattern_ok"] else 1, verify["rows"], verify["entries"]], dtype=torch.int64, device="cuda")
+            dist.all_reduce(bad)
+            errs = torch.tensor([verify["max_err_nz"] if verify["max_err_nz"] is not None else 1e300, verify["max_err_b"]],
+                                dtype=torch.float64, device="cuda")
+            dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+            verify = {"rows": int(bad[1].item()), "entries": int(bad[2].item()), "pattern_ok": int(bad[0].item()) == 0,
+                      "max_err_nz": float(errs[0].item()), "max_err_b": float(errs[1].item())}
+        verify["tol"] = 1e-12
+        verify["ok"] = bool(verify["pattern_ok"] and verify["max_err_nz"] is not None and verify["max_err_nz"] <= 1e-12 and verify["max_err_b"] <= 1e-12)
+        verify["what"] = ("complete lists (minor ids bit-equal, values block-scaled) and residual entries of the sampled owned major dofs "
+                          "vs the oracle's per-cell restatement; sample = random + chunk/strip/interface boundaries + field tails")
+        verify["seconds"] = time.perf_counter() - t0
+
+    # ---- Jacobian-only and residual-only assemblies (a line search calls residual! 1..k times per iteration)
+    def timed(fl, reps=5):
+        for _ in range(2):
+            h.assemble_device(d_x.data_ptr(), d_nz.data_ptr(), d_b.data_ptr(), fl, sync=False)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            h.assemble_device(d_x.data_ptr(), d_nz.data_ptr(), d_b.data_ptr(), fl, sync=False)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ms_jac = timed(capi.GM_JACOBIAN)
+    ms_res = timed(capi.GM_RESIDUAL)
+    parts = {"jacobian_only": {"ms": ms_jac, "Mcells_per_s": sp.model.ncells / (ms_jac * 1e-3) / 1e6},
+             "residual_only": {"ms": ms_res, "Mcells_per_s": sp.model.ncells / (ms_res * 1e-3) / 1e6}}
+
     # ---- e2e through the C ABI with host buffers ----
     e2e = None
     e2e_note = None
@@ -306,11 +360,25 @@ def main():
                "h2d_bytes_per_step": int(tt["h2d_bytes"]), "d2h_bytes_per_step": int(tt["d2h_bytes"]),
                "h2d_ms": tt["h2d_ms"], "kernel_ms": tt["kernel_ms"], "d2h_ms": tt["d2h_ms"], "steps": args.e2e_steps,
                "checksum_match": bool(abs(float(np.abs(bn).sum()) - chk) <= 1e-9 * max(1.0, chk))}
+        # residual-only end to end (iterate H2D + residual D2H): the call a line search repeats
+        ts = []
+        for _ in range(args.e2e_steps + 1):
+            t0 = time.perf_counter()
+            h.assemble(xn, None, bn)
+            ts.append(time.perf_counter() - t0)
+        r_ms = 1e3 * float(np.mean(ts[1:]))
+        if world > 1:
+            t = torch.tensor([r_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            r_ms = float(t.item())
+        tr = h.timing()
+        e2e["residual_only"] = {"value": ncells_total / (r_ms * 1e-3) / 1e6, "unit": "Mcells/s", "ms_per_step": r_ms,
+                                "h2d_bytes_per_step": int(tr["h2d_bytes"]), "d2h_bytes_per_step": int(tr["d2h_bytes"])}
         for arr in pinned:
             capi.host_unregister(arr)
         del nzn
 
-    timing_last = h.timing()
+    timing_last = timing_sync
     # symmetric teardown on every rank BEFORE rank 0 goes on alone (CPU baseline): the library's NCCL
     # communicator and torch's process group are both destroyed collectively
     del d_nz, d_b, d_x
@@ -332,13 +400,17 @@ def main():
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
-            roof["traffic"] = json.load(open(prof)).get(str(args.mesh))
+            tr_ = json.load(open(prof)).get(str(args.mesh))
+            # DRAM bytes of the dominant kernel from the committed `ncu --set full` capture of the 1-GPU run of this mesh
+            # (profile-time figure, not re-measured in this run); a rank of an N-GPU run moves 1/N of it
+            roof["traffic"] = tr_ / world if tr_ else None
+            roof["traffic_note"] = "dram__bytes_read+write of the 1-GPU ncu capture in profiles/, divided by n_gpus"
         except Exception:
             pass
     cpu = None
     if not args.no_cpu:
         N = args.cpu_mesh
-        ncs, ts, thr = cpu_pass(N, prm, 3)
+        ncs, ts, thr = cpu_pass(N, prm, 3, threads=os.cpu_count() or 1)
         cv = ncs / float(np.mean(ts[1:])) / 1e6
         cpu = {"value": cv, "unit": "Mcells/s", "cores": thr, "kind": "port",
                "sample": "%dx%d sub-mesh of the workload, 2 timed passes of the CPU oracle (OpenMP coloured scatter)" % (N, N)}
@@ -351,7 +423,7 @@ def main():
                       "parallelism": ("%d owner-computes row blocks, NCCL send/recv interface-row sum" % world) if world > 1 else "single",
                       "exchange_ms": timing_last.get("exchange_ms"),
                       "pattern_s": t_pattern, "tables_s": t_tables, "device_bytes": info["device_bytes"]},
-           "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "e2e_note": e2e_note, "gpu_launches": int(launches_per_step * args.steps),
+           "roofline": roof, "verify": verify, "parts": parts, "cpu_baseline": cpu, "e2e": e2e, "e2e_note": e2e_note, "gpu_launches": int(launches_per_step * args.steps),
            "clocks": clocks, "ms_per_step_each": per, "checksum_abs_b": chk, "checksum_owned_abs_b": chk_owned}
     print(json.dumps(out))
 

@@ -21,7 +21,7 @@ GM_JACOBIAN, GM_RESIDUAL, GM_CHECK_FINITE, GM_NO_EXCHANGE = 1, 2, 4, 8
 GM_PATH_AUTO, GM_PATH_SCATTER, GM_PATH_CART = 0, 1, 2
 
 EXPORTS = ["gm_version", "gm_last_error", "gm_create", "gm_destroy", "gm_set_params", "gm_pattern",
-           "gm_get_pattern", "gm_assemble", "gm_assemble_device", "gm_host_register", "gm_host_unregister",
+           "gm_get_pattern", "gm_get_rows", "gm_assemble", "gm_assemble_device", "gm_host_register", "gm_host_unregister",
            "gm_set_stream", "gm_timing", "gm_info", "gm_nccl_unique_id", "gm_comm_init",
            "gm_iface_count", "gm_iface_pack", "gm_iface_unpack_add"]
 
@@ -192,6 +192,20 @@ class Handle:
         idx = np.empty(self.nnz, dtype=np.int64) if with_idx else None
         _check(lib().gm_get_pattern(self._h, _p(ptr), _p(idx), C.c_int32(index_base)))
         return ptr, idx
+
+    def get_rows(self, rows, d_nz=0, d_b=0):
+        """Lists of the selected major dofs (0-based global ids): (ptr[nrows+1], idx, val | None, b | None);
+        `d_nz` / `d_b` are DEVICE pointers of the value array / residual to read (0: skipped)."""
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        cap = int(rows.size) * 96 + 64
+        ptr = np.zeros(rows.size + 1, dtype=np.int64)
+        idx = np.zeros(cap, dtype=np.int64)
+        val = np.zeros(cap) if d_nz else None
+        b = np.zeros(rows.size) if d_b else None
+        _check(lib().gm_get_rows(self._h, C.c_int64(rows.size), _p(rows), _p(ptr), _p(idx), _p(val), _p(b), C.c_int64(cap),
+                                 C.c_void_p(d_nz or 0), C.c_void_p(d_b or 0)))
+        n = int(ptr[-1])
+        return ptr, idx[:n], (val[:n] if val is not None else None), b
 
     def assemble(self, x, nzval=None, resid=None, flags=None):
         """Host buffers in/out (numpy float64, C-contiguous)."""

@@ -319,6 +319,67 @@ extern "C" int gm_get_pattern(gm_handle *h, int64_t *ptr, int64_t *idx, int32_t 
   return rc;
 }
 
+// gathers the lists of selected major dofs into dense buffers (one thread block per row)
+__global__ void k_get_rows(int64_t nrows, const int64_t *__restrict__ rows, const int64_t *__restrict__ off,
+                           const int64_t *__restrict__ ptr, const int32_t *__restrict__ idx, const double *__restrict__ nz,
+                           const double *__restrict__ b, int64_t *__restrict__ idx_out, double *__restrict__ val_out,
+                           double *__restrict__ b_out) {
+  const int64_t s = blockIdx.x;
+  if (s >= nrows) return;
+  const int64_t r = rows[s], p0 = ptr[r], len = ptr[r + 1] - p0, o = off[s];
+  for (int64_t k = threadIdx.x; k < len; k += blockDim.x) {
+    if (idx_out) idx_out[o + k] = idx[p0 + k];
+    if (val_out) val_out[o + k] = nz[p0 + k];
+  }
+  if (b_out && threadIdx.x == 0) b_out[s] = b[r];
+}
+__global__ void k_row_lens(int64_t nrows, const int64_t *__restrict__ rows, const int64_t *__restrict__ ptr, int64_t *__restrict__ len) {
+  const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (s < nrows) len[s] = ptr[rows[s] + 1] - ptr[rows[s]];
+}
+
+extern "C" int gm_get_rows(gm_handle *h, int64_t nrows, const int64_t *rows, int64_t *row_ptr, int64_t *idx_out, double *val_out,
+                           double *b_out, int64_t cap, const double *d_nzval, const double *d_resid) {
+  if (!h || !rows || !row_ptr || nrows < 0) { gm_set_error("gm_get_rows: bad argument"); return GM_ERR_ARG; }
+  if (!h->has_pattern) { gm_set_error("gm_get_rows: call gm_pattern first"); return GM_ERR_STATE; }
+  if (idx_out && !h->idx) { gm_set_error("gm_get_rows: the index array was released"); return GM_ERR_STATE; }
+  for (int64_t k = 0; k < nrows; ++k)
+    if (rows[k] < 0 || rows[k] >= h->n_total) { gm_set_error("gm_get_rows: row %lld out of range", (long long)rows[k]); return GM_ERR_ARG; }
+  GM_CUDA(cudaSetDevice(h->dev));
+  row_ptr[0] = 0;
+  if (nrows == 0) return GM_OK;
+  int64_t *d_rows = nullptr, *d_off = nullptr, *d_idx = nullptr;
+  double *d_val = nullptr, *d_b = nullptr;
+  int rc = GM_OK;
+  std::vector<int64_t> len((size_t)nrows);
+#define GR(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { gm_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); rc = e__ == cudaErrorMemoryAllocation ? GM_ERR_OOM : GM_ERR_CUDA; goto done; } } while (0)
+  GR(cudaMalloc(&d_rows, 8 * nrows));
+  GR(cudaMalloc(&d_off, 8 * nrows));
+  GR(cudaMemcpyAsync(d_rows, rows, 8 * nrows, cudaMemcpyHostToDevice, h->stream));
+  k_row_lens<<<gm_blocks(nrows, 256), 256, 0, h->stream>>>(nrows, d_rows, h->ptr, d_off);
+  GR(cudaMemcpyAsync(len.data(), d_off, 8 * nrows, cudaMemcpyDeviceToHost, h->stream));
+  GR(cudaStreamSynchronize(h->stream));
+  for (int64_t k = 0; k < nrows; ++k) row_ptr[k + 1] = row_ptr[k] + len[k];
+  if (row_ptr[nrows] > cap) { gm_set_error("gm_get_rows: %lld entries, capacity %lld", (long long)row_ptr[nrows], (long long)cap); rc = GM_ERR_ARG; goto done; }
+  {
+    const int64_t tot = row_ptr[nrows] > 0 ? row_ptr[nrows] : 1;
+    GR(cudaMemcpyAsync(d_off, row_ptr, 8 * nrows, cudaMemcpyHostToDevice, h->stream));
+    if (idx_out) GR(cudaMalloc(&d_idx, 8 * tot));
+    if (val_out && d_nzval) GR(cudaMalloc(&d_val, 8 * tot));
+    if (b_out && d_resid) GR(cudaMalloc(&d_b, 8 * nrows));
+    k_get_rows<<<(unsigned)nrows, 32, 0, h->stream>>>(nrows, d_rows, d_off, h->ptr, h->idx, d_nzval, d_resid, d_idx, d_val, d_b);
+    GR(cudaGetLastError());
+    if (d_idx) GR(cudaMemcpyAsync(idx_out, d_idx, 8 * row_ptr[nrows], cudaMemcpyDeviceToHost, h->stream));
+    if (d_val) GR(cudaMemcpyAsync(val_out, d_val, 8 * row_ptr[nrows], cudaMemcpyDeviceToHost, h->stream));
+    if (d_b) GR(cudaMemcpyAsync(b_out, d_b, 8 * nrows, cudaMemcpyDeviceToHost, h->stream));
+    GR(cudaStreamSynchronize(h->stream));
+  }
+done:
+#undef GR
+  cudaFree(d_rows); cudaFree(d_off); cudaFree(d_idx); cudaFree(d_val); cudaFree(d_b);
+  return rc;
+}
+
 static int gm_upload_const(gm_handle *h) {
   GmConst &c = h->hc;
   c.Pr = h->prm.Pr; c.Ra = h->prm.Ra; c.n = h->prm.n; c.reg = h->prm.reg;

@@ -152,6 +152,14 @@ int gm_pattern(gm_handle *h, int64_t *nnz);
  * (colptr,rowval) of A, for GM_LAYOUT_CSR (rowptr,colind). */
 int gm_get_pattern(gm_handle *h, int64_t *ptr, int64_t *idx, int32_t index_base);
 
+/* Verification hook (bench.py --verify, tests at sizes where the whole matrix cannot be compared): copies
+ * the lists of `nrows` selected major dofs (0-based global ids) to the host.  row_ptr[nrows+1] receives
+ * offsets into idx_out / val_out (capacity `cap` entries; GM_ERR_ARG if too small), idx_out the minor
+ * ids (0-based), val_out the entries of the DEVICE value array d_nzval (NULL: skipped), b_out[nrows] the
+ * entries of the DEVICE residual d_resid (NULL: skipped).  Same information as A[:, j] / b[j] in Julia. */
+int gm_get_rows(gm_handle *h, int64_t nrows, const int64_t *rows, int64_t *row_ptr, int64_t *idx_out,
+                double *val_out, double *b_out, int64_t cap, const double *d_nzval, const double *d_resid);
+
 /* Replaces jacobian!(A,op,uh) / residual!(b,op,uh) / residual_and_jacobian!(b,A,op,uh).
  * x: n_free_total doubles (host).  nzval: nnz doubles or NULL.  resid: n doubles or NULL.
  * Blocks until the outputs are in host memory. */

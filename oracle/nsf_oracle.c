@@ -372,6 +372,90 @@ int orc_assemble_colored(const orc_problem *P, int transpose, const int64_t *ptr
   return bad ? -1 : 0;
 }
 
+/*
+ * Row oracle (bench.py --verify, tests at the BASELINE sizes): the complete lists of a SAMPLE of
+ * major dofs (CSC columns / CSR rows) -- sorted-unique minor ids, values summed over the incident
+ * cells in cell-id order like the serial scatter above -- and their residual entries, rebuilt
+ * directly from orc_cell.  One pass over the cell table (a byte map marks the sampled dofs), so
+ * it is affordable on the 4096^2 mesh where orc_assemble is not.  `rows` ascending, 0-based global.
+ * out_ptr[nrows+1] are offsets into out_idx/out_val (capacity cap).  Returns the number of
+ * entries, or -1 when cap is too small.  Cells of a row-block rank: every incident cell of an
+ * OWNED dof is in the local table (owned rows + upper ghost row), so the lists are complete.
+ */
+typedef struct { int64_t slot; int64_t minor; int64_t seq; double v; } orc_trip;
+static int cmp_trip(const void *a, const void *b) {
+  const orc_trip *x = (const orc_trip *)a, *y = (const orc_trip *)b;
+  if (x->slot != y->slot) return x->slot < y->slot ? -1 : 1;
+  if (x->minor != y->minor) return x->minor < y->minor ? -1 : 1;
+  return x->seq < y->seq ? -1 : (x->seq > y->seq ? 1 : 0);
+}
+int64_t orc_rows(const orc_problem *P, int transpose, int64_t nrows, const int64_t *rows, const double *x,
+                 int64_t *out_ptr, int64_t *out_idx, double *out_val, double *out_b, int64_t cap) {
+  const int ld = ld_of(P);
+  const int64_t n = P->n_free[0] + P->n_free[1] + P->n_free[2];
+  unsigned char *mark = (unsigned char *)calloc((size_t)n + 1, 1);
+  for (int64_t k = 0; k < nrows; ++k) mark[rows[k]] = 1;
+  int64_t tcap = nrows * 4 * ld + 64, nt = 0, seq = 0;
+  orc_trip *t = (orc_trip *)malloc(sizeof(orc_trip) * (size_t)tcap);
+  if (out_b) for (int64_t k = 0; k < nrows; ++k) out_b[k] = 0.0;
+  double r[MAXLD], J[MAXLD * MAXLD];
+  int64_t ids[MAXLD];
+  for (int64_t c = 0; c < P->ncells; ++c) {
+    cell_ids(P, c, ids);
+    int hit = 0;
+    for (int l = 0; l < ld; ++l)
+      if (ids[l] > 0 && mark[ids[l] - 1]) { hit = 1; break; }
+    if (!hit) continue;
+    orc_cell(P, c, x, r, J);
+    for (int M = 0; M < ld; ++M) {
+      if (ids[M] <= 0 || !mark[ids[M] - 1]) continue;
+      /* slot of this major in rows[] (binary search) */
+      int64_t lo = 0, hi = nrows - 1, slot = -1;
+      while (lo <= hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (rows[mid] < ids[M] - 1) lo = mid + 1; else if (rows[mid] > ids[M] - 1) hi = mid - 1; else { slot = mid; break; }
+      }
+      if (out_b) out_b[slot] += r[M];
+      const int fM = field_of(P, M);
+      for (int m = 0; m < ld; ++m) {
+        if (ids[m] <= 0) continue;
+        const int fm = field_of(P, m);
+        /* CSC: major = trial column j, minor = test row i ; CSR: major = test row, minor = trial col */
+        const int ok = transpose ? touched(fM, fm) : touched(fm, fM);
+        if (!ok) continue;
+        if (nt == tcap) { tcap *= 2; t = (orc_trip *)realloc(t, sizeof(orc_trip) * (size_t)tcap); }
+        t[nt].slot = slot; t[nt].minor = ids[m] - 1; t[nt].seq = seq++;
+        t[nt].v = transpose ? J[M * ld + m] : J[m * ld + M];
+        ++nt;
+      }
+    }
+  }
+  qsort(t, (size_t)nt, sizeof(orc_trip), cmp_trip);
+  int64_t nout = 0, k = 0;
+  for (int64_t s = 0; s < nrows; ++s) {
+    out_ptr[s] = nout;
+    while (k < nt && t[k].slot == s) {
+      const int64_t minor = t[k].minor;
+      double v = 0.0;
+      while (k < nt && t[k].slot == s && t[k].minor == minor) v += t[k++].v;
+      if (nout >= cap) { free(t); free(mark); return -1; }
+      out_idx[nout] = minor; out_val[nout] = v; ++nout;
+    }
+  }
+  out_ptr[nrows] = nout;
+  free(t); free(mark);
+  return nout;
+}
+
+/* torchrun pins OMP_NUM_THREADS=1 in its workers; bench.py's cpu_baseline leg asks for every host core */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -47,6 +47,7 @@ def _lib():
         _LIB.orc_assemble.restype = C.c_int
         _LIB.orc_assemble_colored.restype = C.c_int
         _LIB.orc_num_threads.restype = C.c_int
+        _LIB.orc_rows.restype = C.c_int64
     return _LIB
 
 
@@ -124,6 +125,29 @@ class Oracle:
         if rc != 0:
             raise RuntimeError("oracle: entry missing from pattern")
         return nz, b
+
+    def rows(self, rows, x, layout="csc"):
+        """Row oracle: complete lists (sorted-unique minor ids, values) and residual entries of the
+        sampled major dofs `rows` (ascending, 0-based global), rebuilt from orc_cell over the incident cells.
+        Returns (ptr[nrows+1], idx, val, b)."""
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        assert rows.size == 0 or np.all(np.diff(rows) > 0)
+        tr = 1 if layout == "csr" else 0
+        cap = int(rows.size) * 96 + 64
+        ptr = np.zeros(rows.size + 1, dtype=np.int64)
+        idx = np.zeros(cap, dtype=np.int64)
+        val = np.zeros(cap)
+        b = np.zeros(rows.size)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        n = _lib().orc_rows(C.byref(self.P), tr, C.c_int64(rows.size), _p(rows), _p(x), _p(ptr), _p(idx), _p(val), _p(b),
+                            C.c_int64(cap))
+        if n < 0:
+            raise RuntimeError("oracle: row buffer too small")
+        return ptr, idx[:n], val[:n], b
+
+    @staticmethod
+    def set_num_threads(n):
+        _lib().orc_set_num_threads(C.c_int(int(n)))
 
     @staticmethod
     def num_threads():

@@ -139,26 +139,62 @@ def test_structured_path_other_kernels(gm, gpu_lib, monkeypatch, kernel, case, l
         _check(gm, sp, PARAMS[pi], layout, gm.capi.GM_PATH_CART, x)
 
 
-def test_structured_equals_scatter_256(gm, gpu_lib):
-    """Config 2 (256x256, n=0.6, Ra=1e5, Pr=100): both CUDA paths agree to 1e-13 (block scaled);
-    too large for the oracle's serial scatter to stay in the seconds range on pytest's budget."""
+def test_config2_256_matches_oracle(gm, gpu_lib):
+    """Config 2 (256x256 quads, turan BCs, n=0.6, Ra=1e5, Pr=100; nnz = 44,511,759): the structured
+    kernel against the oracle's full serial assembly -- pattern bit-exact, every entry within 1e-12 block-scaled --
+    and the generic scatter path against the same numbers."""
     sp = cases.cart(256, bc=cases.TURAN)
     x = fe.splitmix_iterate(sp.n_total, 1234)
-    out = {}
-    for path in (gm.capi.GM_PATH_SCATTER, gm.capi.GM_PATH_CART):
+    orc = Oracle(sp, **PARAMS[1])
+    optr, oidx = orc.pattern("csc")
+    onz, ob = orc.assemble(x, "csc")
+    assert oidx.size == 44511759
+    blocks, rblocks = cases.nz_blocks(sp, optr, oidx), cases.res_blocks(sp)
+    for path in (gm.capi.GM_PATH_CART, gm.capi.GM_PATH_SCATTER):
         h = gm.capi.Handle(sp, layout="csc", path=path)
         h.set_params(**PARAMS[1])
         nnz = h.pattern()
-        assert nnz == 44511759  # SURVEY Appendix B
+        assert nnz == 44511759
         nz, b = np.empty(nnz), np.empty(sp.n_total)
         h.assemble(x, nz, b)
         ptr, idx = h.get_pattern()
-        out[path] = (nz, b, ptr, idx)
         h.close()
-    a, c = out[gm.capi.GM_PATH_SCATTER], out[gm.capi.GM_PATH_CART]
-    assert np.array_equal(a[2], c[2]) and np.array_equal(a[3], c[3])
-    assert cases.block_scaled_err(c[0], a[0], cases.nz_blocks(sp, a[2], a[3])) <= 1e-13
-    assert cases.block_scaled_err(c[1], a[1], cases.res_blocks(sp)) <= 1e-13
+        assert np.array_equal(ptr, optr) and np.array_equal(idx, oidx)
+        assert cases.block_scaled_err(nz, onz, blocks) <= TOL
+        assert cases.block_scaled_err(b, ob, rblocks) <= TOL
+
+
+@pytest.mark.parametrize("N,pi,layout", [(2048, 1, "csc"), (1100, 2, "csr")])
+def test_bench_sizes_row_oracle(gm, gpu_lib, N, pi, layout):
+    """Config 4 (2048x2048, n=0.6: nnz = 2,866,381,327 > 2^31, 9 x 257 CTAs of the 256-column k-chunk build that
+    bench.py times) and a ragged 1100x1100 CSR case: complete lists of ~10^4 sampled major dofs (chunk / strip
+    boundaries, field tails with the largest 64-bit list bases, random) against the row oracle.  bench.py --verify runs
+    the same check at 4096^2 and on every rank of the multi-GPU runs."""
+    import torch
+    import rowcheck
+    sp = cases.cart(N, bc=cases.TURAN)
+    prm = PARAMS[pi]
+    x = fe.splitmix_iterate(sp.n_total, 1234)
+    h = gm.capi.Handle(sp, layout=layout, path=gm.capi.GM_PATH_CART)
+    try:
+        h.set_params(**prm)
+        nnz = h.pattern()
+        assert nnz == 684 * N * N - 1232 * N + 527  # SURVEY A.5 closed form (turan BCs)
+        dx = torch.from_numpy(x).cuda()
+        dnz = torch.full((nnz,), float("nan"), dtype=torch.float64, device="cuda")
+        db = torch.full((sp.n_total,), float("nan"), dtype=torch.float64, device="cuda")
+        h.assemble_device(dx.data_ptr(), dnz.data_ptr(), db.data_ptr(), gm.capi.GM_JACOBIAN | gm.capi.GM_RESIDUAL, sync=True)
+        assert not bool(torch.isnan(dnz).any()) and not bool(torch.isnan(db).any()), "every entry must be written"
+        rows = rowcheck.sample_rows(sp, nrandom=3000)
+        out = rowcheck.check_rows(sp, h, Oracle(sp, **prm), x, dnz.data_ptr(), db.data_ptr(), layout, rows)
+        ptr_tail = h.get_rows(rows[-1:])[0]
+        assert out["pattern_ok"], out
+        assert out["max_err_nz"] <= TOL and out["max_err_b"] <= TOL, out
+        assert out["rows"] >= 5000
+        if N == 2048:
+            assert nnz > 2 ** 31 and ptr_tail[-1] > 0
+    finally:
+        h.close()
 
 
 @pytest.mark.parametrize("nranks,nx,ny", [(2, 9, 8), (3, 70, 19), (4, 6, 4)])

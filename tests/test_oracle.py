@@ -112,3 +112,21 @@ def test_colored_oracle_equals_serial():
     ptr, idx = orc.pattern()
     assert cases.block_scaled_err(a2, a, cases.nz_blocks(sp, ptr, idx)) < 1e-13
     assert cases.block_scaled_err(b2, b, cases.res_blocks(sp)) < 1e-13
+
+
+@pytest.mark.parametrize("layout", ["csc", "csr"])
+def test_row_oracle_equals_full_assembly(layout):
+    """orc_rows (the sampled row oracle of bench.py --verify / tests at the BASELINE sizes) rebuilds exactly the
+    lists of orc_pattern / orc_assemble: same minor ids, bit-equal values (same cell order of the sums)."""
+    import rowcheck
+    for sp in (cases.cart(13, 7, bc=cases.TURAN), cases.spaces(fe.annulus_model(nr=3, nt=12, jitter=0.2, seed=3), cases.KUEHN)):
+        prm = dict(Pr=100.0, Ra=1e5, n=0.6)
+        orc = Oracle(sp, **prm)
+        x = fe.splitmix_iterate(sp.n_total, 1234)
+        ptr, idx = orc.pattern(layout)
+        nz, b = orc.assemble(x, layout)
+        for rows in (np.arange(sp.n_total), rowcheck.sample_rows(sp, nrandom=50)):
+            rp, ri, rv, rb = orc.rows(rows, x, layout)
+            assert np.array_equal(np.diff(rp), ptr[rows + 1] - ptr[rows])
+            sel = np.concatenate([np.arange(ptr[r], ptr[r + 1]) for r in rows])
+            assert np.array_equal(ri, idx[sel]) and np.array_equal(rv, nz[sel]) and np.array_equal(rb, b[rows])
