@@ -155,6 +155,8 @@ def main():
     ap.add_argument("--power-index", dest="n", type=float, default=0.0, help="power-law index n (default 0.6; 1.4 for N>1)")
     ap.add_argument("--layout", default="csc", choices=["csc", "csr"])
     ap.add_argument("--path", default="auto", choices=["auto", "scatter", "cart"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "mma", "gath", "gath1", "sweep"], help="structured-path kernel generation (A/B)")
+    ap.add_argument("--xchunk", type=int, default=0, help="quad columns per x-chunk (0: chosen by the library)")
     ap.add_argument("--cpu-mesh", type=int, default=512)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
@@ -198,7 +200,9 @@ def main():
     x_host = gm.fe.splitmix_iterate(sp.n_total, 1234)
     t_tables = time.perf_counter() - t0
     pathid = {"auto": capi.GM_PATH_AUTO, "scatter": capi.GM_PATH_SCATTER, "cart": capi.GM_PATH_CART}[args.path]
-    h = capi.Handle(sp, layout=args.layout, device=local, path=pathid, rank=rank, nranks=world)
+    kid = {"auto": capi.GM_KERNEL_AUTO, "mma": capi.GM_KERNEL_MMA, "gath": capi.GM_KERNEL_GATH, "gath1": capi.GM_KERNEL_GATH1,
+           "sweep": capi.GM_KERNEL_SWEEP}[args.kernel]
+    h = capi.Handle(sp, layout=args.layout, device=local, path=pathid, rank=rank, nranks=world, kernel=kid, xchunk=args.xchunk)
     h.set_params(**prm)
     t0 = time.perf_counter()
     nnz = h.pattern()
@@ -418,7 +422,7 @@ def main():
            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
            "data": "synthetic",
            "config": {"workload": workload_name(args), "ncells": sp.model.ncells, "n_free": sp.n_total, "nnz": nnz_global, "nnz_local": nnz,
-                      "layout": args.layout, "path": {1: "scatter", 2: "cart"}[info["active_path"]],
+                      "layout": args.layout, "path": {1: "scatter", 2: "cart"}[info["active_path"]], "kernel": args.kernel,
                       "l2": "outputs (%.1f GB) exceed L2 by >100x; no flush needed" % (8 * nnz / 1e9),
                       "parallelism": ("%d owner-computes row blocks, NCCL send/recv interface-row sum" % world) if world > 1 else "single",
                       "exchange_ms": timing_last.get("exchange_ms"),

@@ -19,6 +19,7 @@ GM_QUAD, GM_TRI = 0, 1
 GM_LAYOUT_CSC, GM_LAYOUT_CSR = 0, 1
 GM_JACOBIAN, GM_RESIDUAL, GM_CHECK_FINITE, GM_NO_EXCHANGE = 1, 2, 4, 8
 GM_PATH_AUTO, GM_PATH_SCATTER, GM_PATH_CART = 0, 1, 2
+GM_KERNEL_AUTO, GM_KERNEL_MMA, GM_KERNEL_GATH, GM_KERNEL_GATH1, GM_KERNEL_SWEEP = 0, 1, 2, 3, 4
 
 EXPORTS = ["gm_version", "gm_last_error", "gm_create", "gm_destroy", "gm_set_params", "gm_pattern",
            "gm_get_pattern", "gm_get_rows", "gm_assemble", "gm_assemble_device", "gm_host_register", "gm_host_unregister",
@@ -49,6 +50,7 @@ class gm_desc(C.Structure):
         ("rank", C.c_int32), ("nranks", C.c_int32),
         ("cell_begin", C.c_int64), ("ncells_global", C.c_int64),
         ("ghost_lo", C.c_int32), ("ghost_hi", C.c_int32),
+        ("kernel", C.c_int32), ("xchunk", C.c_int32),
     ]
 
 
@@ -113,7 +115,7 @@ def _p(a):
 class Handle:
     """Owns one gm_handle."""
 
-    def __init__(self, sp, layout="csc", device=0, path=GM_PATH_AUTO, rank=0, nranks=1):
+    def __init__(self, sp, layout="csc", device=0, path=GM_PATH_AUTO, rank=0, nranks=1, kernel=GM_KERNEL_AUTO, xchunk=0):
         """`sp` from fe.build_spaces (whole mesh) or fe.build_rank_spaces (one row block of `nranks`)."""
         m, r = sp.model, sp.ref
         c = np.ascontiguousarray
@@ -154,6 +156,7 @@ class Handle:
         keep["w"], keep["phi"], keep["dphi"], keep["psi"], keep["dgphi"] = c(r.w), c(r.phi), c(r.dphi), c(r.psi), c(r.dgphi)
         d.w, d.phi, d.dphi, d.psi, d.dgphi = _p(keep["w"]), _p(keep["phi"]), _p(keep["dphi"]), _p(keep["psi"]), _p(keep["dgphi"])
         d.device, d.path = device, path
+        d.kernel, d.xchunk = kernel, xchunk
         d.rank, d.nranks, d.ncells_global = rank, nranks, m.ncells
         if rows is None:
             d.cell_begin = 0

@@ -74,10 +74,12 @@ struct gm_cart {
   gm_params last_prm;
   bool tab_valid = false;
   int th = 8;  // cell rows per strip (template parameter of k_cart)
-  // kernel selection, read from the environment when the handle is created (A/B measurements and tests):
-  // GM_CART_KERNEL=sweep -> first-generation k_cart (gm_cart_kernel.cuh); default: k_gath (gm_gath_kernel.cuh)
+  // kernel generation (gm_desc.kernel): GM_KERNEL_MMA (default) k_mma, GM_KERNEL_GATH / GM_KERNEL_GATH1 k_gath with
+  // two / one trio of matrix warps, GM_KERNEL_SWEEP first-generation k_cart.  The older kernels stay selectable for A/B
+  // measurements and are parity-tested.
+  int kernel = GM_KERNEL_MMA;
   bool use_sweep = false;
-  int gath_ng = 2;  // GM_GATH_NG: trios of matrix warps per CTA (1 or 2)
+  int gath_ng = 2;
 };
 
 
@@ -201,6 +203,7 @@ __global__ void k_ct_visc(int64_t ncells, const int32_t *__restrict__ g, const d
 
 #include "gm_cart_kernel.cuh"
 #include "gm_gath_kernel.cuh"
+#include "gm_mma_kernel.cuh"
 
 // ------------------------------------------------------------------------------------------
 // host side
@@ -218,12 +221,9 @@ static int gm_cart_create(gm_handle *h) {
   gm_cart *c = new (std::nothrow) gm_cart();
   if (!c) return GM_ERR_OOM;
   h->cart = c;
-  {
-    const char *e = getenv("GM_CART_KERNEL");
-    c->use_sweep = e && strcmp(e, "sweep") == 0;
-    e = getenv("GM_GATH_NG");
-    c->gath_ng = (e && atoi(e) == 1) ? 1 : 2;
-  }
+  c->kernel = h->d.kernel == GM_KERNEL_AUTO ? GM_KERNEL_MMA : h->d.kernel;
+  c->use_sweep = c->kernel == GM_KERNEL_SWEEP;
+  c->gath_ng = c->kernel == GM_KERNEL_GATH1 ? 1 : 2;
   h->active_path = GM_PATH_CART;  // confirmed (or revoked) by gm_cart_after_pattern
   return GM_OK;
 }
@@ -324,12 +324,9 @@ static int gm_cart_tables(gm_handle *h) {
 
 template <int TH, bool CSR, bool NEWT>
 static int gm_cart_launch1(gm_handle *h, const CartArgs &a) {
-  static bool attr_set = false;
   const size_t sm = sizeof(CtSmem<TH>);
-  if (!attr_set) {
-    GM_CUDA(cudaFuncSetAttribute(k_cart<TH, CSR, NEWT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    attr_set = true;
-  }
+  // per-DEVICE attribute: set on every launch (a process may hold handles on several devices)
+  GM_CUDA(cudaFuncSetAttribute(k_cart<TH, CSR, NEWT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   dim3 grid((a.nx + CT_XCH - 1) / CT_XCH, (a.row_end - a.row_begin + TH - 1) / TH);
   k_cart<TH, CSR, NEWT><<<grid, (3 * TH / 2 + 2) * 32, sm, h->stream>>>(a);
   return GM_OK;
@@ -343,12 +340,8 @@ static int gm_cart_launch(gm_handle *h, const CartArgs &a, bool csr, bool newt) 
 // ---- k_gath (gm_gath_kernel.cuh): NG trios of matrix warps + GA_NAUX aux warps, one CTA per SM
 template <int NG, bool CSR, bool NEWT, int XCH>
 static int gm_gath_launch2(gm_handle *h, const CartArgs &a, int nstrips) {
-  static bool attr_set = false;
   const size_t sm = sizeof(GaSmem<NG>);
-  if (!attr_set) {
-    GM_CUDA(cudaFuncSetAttribute(k_gath<NG, CSR, NEWT, XCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    attr_set = true;
-  }
+  GM_CUDA(cudaFuncSetAttribute(k_gath<NG, CSR, NEWT, XCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
   dim3 grid((a.nx + 1 + XCH - 1) / XCH, nstrips);
   k_gath<NG, CSR, NEWT, XCH><<<grid, (3 * NG + GA_NAUX) * 32, sm, h->stream>>>(a);
   return GM_OK;
@@ -356,13 +349,37 @@ static int gm_gath_launch2(gm_handle *h, const CartArgs &a, int nstrips) {
 template <int NG, bool CSR, bool NEWT>
 static int gm_gath_launch1(gm_handle *h, const CartArgs &a) {
   const int nstrips = (a.row_end - a.row_begin + 1 + 4 * NG - 1) / (4 * NG);
-  return gm_gath_chunk(a.nx, nstrips, h->num_sms) == 128 ? gm_gath_launch2<NG, CSR, NEWT, 128>(h, a, nstrips)
-                                                         : gm_gath_launch2<NG, CSR, NEWT, 256>(h, a, nstrips);
+  const int xch = h->d.xchunk ? h->d.xchunk : gm_gath_chunk(a.nx, nstrips, h->num_sms);
+  return xch <= 128 ? gm_gath_launch2<NG, CSR, NEWT, 128>(h, a, nstrips) : gm_gath_launch2<NG, CSR, NEWT, 256>(h, a, nstrips);
 }
 template <int NG>
 static int gm_gath_launch(gm_handle *h, const CartArgs &a, bool csr, bool newt) {
   if (csr) return newt ? gm_gath_launch1<NG, true, true>(h, a) : gm_gath_launch1<NG, true, false>(h, a);
   return newt ? gm_gath_launch1<NG, false, true>(h, a) : gm_gath_launch1<NG, false, false>(h, a);
+}
+
+// ---- k_mma (gm_mma_kernel.cuh): 4 main + 4 aux warps, 8 quad rows, two CTAs per SM
+template <bool CSR, bool NEWT, int XCH>
+static int gm_mma_launch2(gm_handle *h, const CartArgs &a, int nstrips) {
+  const size_t sm = sizeof(MmSmem);
+  GM_CUDA(cudaFuncSetAttribute(k_mma<CSR, NEWT, XCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));  // (per device: set on every launch)
+  MmArgs ma;
+  ma.a = a;
+  memcpy(ma.out, MM_OUT, sizeof ma.out);
+  dim3 grid((a.nx + 1 + XCH - 1) / XCH, nstrips);
+  k_mma<CSR, NEWT, XCH><<<grid, MM_NT, sm, h->stream>>>(ma);
+  return GM_OK;
+}
+template <bool CSR, bool NEWT>
+static int gm_mma_launch1(gm_handle *h, const CartArgs &a, int xch) {
+  const int nstrips = (a.row_end - a.row_begin + 1 + MM_QH - 1) / MM_QH;
+  if (xch == 0) xch = gm_gath_chunk(a.nx, nstrips, 2 * h->num_sms);
+  return xch <= 32 ? gm_mma_launch2<CSR, NEWT, 32>(h, a, nstrips)
+         : xch <= 128 ? gm_mma_launch2<CSR, NEWT, 128>(h, a, nstrips) : gm_mma_launch2<CSR, NEWT, 256>(h, a, nstrips);
+}
+static int gm_mma_launch(gm_handle *h, const CartArgs &a, bool csr, bool newt, int xch) {
+  if (csr) return newt ? gm_mma_launch1<true, true>(h, a, xch) : gm_mma_launch1<true, false>(h, a, xch);
+  return newt ? gm_mma_launch1<false, true>(h, a, xch) : gm_mma_launch1<false, false>(h, a, xch);
 }
 
 static int gm_cart_run(gm_handle *h, const double *d_x, double *d_nz, double *d_b, unsigned flags, int64_t *launches) {
@@ -382,7 +399,8 @@ static int gm_cart_run(gm_handle *h, const double *d_x, double *d_nz, double *d_
     ++*launches;
   }
   const bool csr = h->d.layout == GM_LAYOUT_CSR;
-  if (c->use_sweep) rc = gm_cart_launch<4>(h, a, csr, newt);
+  if (c->kernel == GM_KERNEL_MMA) rc = gm_mma_launch(h, a, csr, newt, h->d.xchunk);
+  else if (c->use_sweep) rc = gm_cart_launch<4>(h, a, csr, newt);
   else rc = c->gath_ng == 1 ? gm_gath_launch<1>(h, a, csr, newt) : gm_gath_launch<2>(h, a, csr, newt);
   if (rc) return rc;
   ++*launches;

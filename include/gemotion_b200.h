@@ -68,6 +68,15 @@ enum gm_path {
   GM_PATH_CART = 2     /* structured owner-computes row gather, Cartesian quads only */
 };
 
+/* Kernel generation of the structured path (A/B measurements, parity tests of the older generations) */
+enum gm_kernel {
+  GM_KERNEL_AUTO = 0,  /* the fastest one: GM_KERNEL_MMA */
+  GM_KERNEL_MMA = 1,   /* fp64 tensor-pipe formulation (k_mma) */
+  GM_KERNEL_GATH = 2,  /* register gather (k_gath), two trios of matrix warps */
+  GM_KERNEL_GATH1 = 3, /* register gather, one trio */
+  GM_KERNEL_SWEEP = 4  /* first generation shared-memory sweep (k_cart) */
+};
+
 typedef struct gm_handle gm_handle;
 
 /*
@@ -116,6 +125,9 @@ typedef struct gm_desc {
    * above the owned rows (0 or 1 each; ny counts all local rows).  Ghost cells only complete the
    * symbolic pattern of the interface rows; they are never assembled. */
   int32_t ghost_lo, ghost_hi;
+  /* structured path: kernel generation (gm_kernel) and quad columns per x-chunk (0 = chosen from the grid size; tests
+   * force 32 / 128 / 256 to put chunk seams on small meshes) */
+  int32_t kernel, xchunk;
 } gm_desc;
 
 /* Timings of the last gm_assemble / gm_assemble_device call, milliseconds, CUDA events on the

@@ -8,6 +8,7 @@
 // poisoned at block start.
 #pragma once
 #include <pthread.h>
+#include <sched.h>
 #include <stdint.h>
 #include <string.h>
 
@@ -21,6 +22,7 @@
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
+#define __constant__
 #define __maxnreg__(...)
 #define __restrict__
 #define __align__(x)
@@ -53,6 +55,43 @@ static inline double ga_shfl_xor(double v, int mask) {
   const double r = g_emu_xbuf[w][l ^ mask];
   pthread_barrier_wait(&g_emu_bar_warp[w]);
   return r;
+}
+
+// ---- fp64 tensor instruction mma.sync.m8n8k4 (k_mma): all 32 threads of the warp must call it.
+// Fragments as in PTX: A[row = lane / 4][k = lane % 4], B[k = lane % 4][col = lane / 4], D[row = lane / 4][col = 2 (lane % 4) + {0, 1}].
+static double g_emu_ma[64][32], g_emu_mb[64][32];
+static inline void mm_dmma(double (&d)[2], double a, double b) {
+  const unsigned w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  g_emu_ma[w][l] = a; g_emu_mb[w][l] = b;
+  pthread_barrier_wait(&g_emu_bar_warp[w]);
+  const unsigned g = l >> 2, j = l & 3;
+  for (int c = 0; c < 2; ++c) {
+    double acc = d[c];
+    for (int k = 0; k < 4; ++k) acc = fma(g_emu_ma[w][4 * g + k], g_emu_mb[w][4 * (2 * j + c) + k], acc);
+    d[c] = acc;
+  }
+  pthread_barrier_wait(&g_emu_bar_warp[w]);
+}
+// ---- mbarrier: low half = pending arrivals, high half = parity of the current (incomplete) phase
+static int g_emu_mbar_count = 0;
+static inline void mm_mbar_init(unsigned long long *bar, int count) { g_emu_mbar_count = count; __atomic_store_n(bar, (unsigned long long)count, __ATOMIC_RELEASE); }
+static inline void mm_mbar_arrive(unsigned long long *bar) {
+  unsigned long long old = __atomic_load_n(bar, __ATOMIC_ACQUIRE), nw;
+  do {
+    unsigned pend = (unsigned)old - 1, ph = (unsigned)(old >> 32);
+    if (pend == 0) { pend = (unsigned)g_emu_mbar_count; ph ^= 1; }
+    nw = ((unsigned long long)ph << 32) | pend;
+  } while (!__atomic_compare_exchange_n(bar, &old, nw, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE));
+}
+static inline void mm_mbar_wait(unsigned long long *bar, unsigned parity) {
+  while ((unsigned)(__atomic_load_n(bar, __ATOMIC_ACQUIRE) >> 32) == parity) sched_yield();
+}
+static inline double mm_mask(double v, uint32_t mw, uint32_t sign) {
+  uint64_t b;
+  memcpy(&b, &v, 8);
+  b = (((b >> 32) & mw) ^ sign) << 32 | ((uint32_t)b & mw);
+  memcpy(&v, &b, 8);
+  return v;
 }
 
 struct EmuCopy { void *dst; const void *src; int bytes; };

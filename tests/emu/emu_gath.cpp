@@ -4,6 +4,7 @@
 
 #include "../../gemotion.jl_b200/csrc/gm_cart_tables.h"
 #include "../../gemotion.jl_b200/csrc/gm_gath_kernel.cuh"
+#include "../../gemotion.jl_b200/csrc/gm_mma_kernel.cuh"
 
 // viscosity pre-pass, same arithmetic as k_ct_visc (gm_cart.cuh)
 static void emu_visc(int64_t ncells, const int32_t *g, const double *dvals, const double *x, const CartCell *cc, double reg,
@@ -35,6 +36,17 @@ static int run(CartArgs a, bool csr, bool newt) {
   return newt ? emu_launch(k_gath<NG, false, true, XCH>, a, gx, gy, nt, GA_NAUX * 32, sm) : emu_launch(k_gath<NG, false, false, XCH>, a, gx, gy, nt, GA_NAUX * 32, sm);
 }
 
+template <int XCH>
+static int run_mma(const CartArgs &a, bool csr, bool newt) {
+  MmArgs ma;
+  ma.a = a;
+  memcpy(ma.out, MM_OUT, sizeof ma.out);
+  const unsigned gx = (a.nx + 1 + XCH - 1) / XCH, gy = (a.row_end - a.row_begin + 1 + MM_QH - 1) / MM_QH;
+  const size_t sm = sizeof(MmSmem);
+  if (csr) return newt ? emu_launch(k_mma<true, true, XCH>, ma, gx, gy, MM_NT, MM_NAW * 32, sm) : emu_launch(k_mma<true, false, XCH>, ma, gx, gy, MM_NT, MM_NAW * 32, sm);
+  return newt ? emu_launch(k_mma<false, true, XCH>, ma, gx, gy, MM_NT, MM_NAW * 32, sm) : emu_launch(k_mma<false, false, XCH>, ma, gx, gy, MM_NT, MM_NAW * 32, sm);
+}
+
 extern "C" int emu_gath_run(int nx, int ny, int row_begin, int row_end, const int32_t *gdofs, const double *dvals,
                             const int64_t *ptr, const int32_t *cls, int nclass, const uint8_t *ctab, const double *x, double *nz,
                             double *b, unsigned flags, int csr, const double *prm /*Pr Ra n reg gx gy js*/, double hx, double hy,
@@ -54,6 +66,11 @@ extern "C" int emu_gath_run(int nx, int ny, int row_begin, int row_end, const in
   a.tab = tab; a.cc = &cell; a.x = x; a.nz = nz; a.b = b; a.flags = flags;
   a.Pr = prm[0]; a.RaPr = prm[1] * prm[0]; a.gx = prm[4]; a.gy = prm[5]; a.reg = prm[3]; a.n = prm[2]; a.js = prm[6];
   g_emu_bulk_misaligned = 0;
+  if (ng == 0) {  // k_mma (gm_mma_kernel.cuh)
+    int rc = xch == 256 ? run_mma<256>(a, csr != 0, newt) : (xch == 128 ? run_mma<128>(a, csr != 0, newt) : run_mma<32>(a, csr != 0, newt));
+    if (diag) diag[0] = g_emu_bulk_misaligned;
+    return rc;
+  }
   // the configurations the library instantiates (x-chunks of 256 / 128 columns), plus 32-column chunks to exercise chunk seams on small meshes
   int rc = ng == 1 ? (xch == 256 ? run<1, 256>(a, csr != 0, newt) : (xch == 128 ? run<1, 128>(a, csr != 0, newt) : run<1, 32>(a, csr != 0, newt)))
                    : (xch == 256 ? run<2, 256>(a, csr != 0, newt) : (xch == 128 ? run<2, 128>(a, csr != 0, newt) : run<2, 32>(a, csr != 0, newt)));

@@ -24,6 +24,8 @@ def _build():
     so = os.path.join(EMU_DIR, "_emu_gath.so")
     srcs = [os.path.join(EMU_DIR, "emu_gath.cpp"), os.path.join(EMU_DIR, "cuda_emu.h"),
             os.path.join(ROOT, "gemotion.jl_b200", "csrc", "gm_gath_kernel.cuh"),
+            os.path.join(ROOT, "gemotion.jl_b200", "csrc", "gm_mma_kernel.cuh"),
+            os.path.join(ROOT, "gemotion.jl_b200", "csrc", "gm_mma_tiles.h"),
             os.path.join(ROOT, "gemotion.jl_b200", "csrc", "gm_cart_tables.h")]
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-pthread", "-Wno-unknown-pragmas",
@@ -140,33 +142,38 @@ CART_CASES = [
 ]
 
 
+@pytest.mark.parametrize("kernel", ["mma", "gath"])
 @pytest.mark.parametrize("case", CART_CASES, ids=[c[0] for c in CART_CASES])
 @pytest.mark.parametrize("pi", range(len(PARAMS)))
 @pytest.mark.parametrize("layout", ["csc", "csr"])
-def test_gather_kernel_logic_matches_oracle(emu, case, pi, layout):
+def test_gather_kernel_logic_matches_oracle(emu, kernel, case, pi, layout):
+    """`ng` = 0 selects k_mma (gm_mma_kernel.cuh: the tensor instruction, the mbarrier and the warp roles are emulated
+    by cuda_emu.h), 1 / 2 the trios of k_gath."""
     _, nx, ny, bc = case
     sp = cases.cart(nx, ny, bc=bc, domain=(0, 1.5, 0, 1))
     x = fe.splitmix_iterate(sp.n_total, 1234)
-    orc, ptr, idx, nz, b, _ = run_emu(emu, sp, PARAMS[pi], layout, x, ng=1 + (pi % 2), xch=(256, 128, 32)[pi])
+    orc, ptr, idx, nz, b, _ = run_emu(emu, sp, PARAMS[pi], layout, x, ng=0 if kernel == "mma" else 1 + (pi % 2), xch=(256, 128, 32)[pi])
     onz, ob = orc.assemble(x, layout)
     assert not np.isnan(nz).any() and not np.isnan(b).any(), "every list position / residual entry must be written"
     assert cases.block_scaled_err(nz, onz, cases.nz_blocks(sp, ptr, idx)) <= TOL
     assert cases.block_scaled_err(b, ob, cases.res_blocks(sp)) <= TOL
 
 
-def test_gather_kernel_jacobian_only_and_residual_only(emu):
+@pytest.mark.parametrize("ng", [0, 2], ids=["mma", "gath"])
+def test_gather_kernel_jacobian_only_and_residual_only(emu, ng):
     sp = cases.cart(6, 5, bc=cases.TURAN)
     x = fe.splitmix_iterate(sp.n_total, 7)
-    _, _, _, nz, b, _ = run_emu(emu, sp, PARAMS[1], "csc", x)
-    _, _, _, nz1, b1, _ = run_emu(emu, sp, PARAMS[1], "csc", x, flags=1)
-    _, _, _, nz2, b2, _ = run_emu(emu, sp, PARAMS[1], "csc", x, flags=2)
+    _, _, _, nz, b, _ = run_emu(emu, sp, PARAMS[1], "csc", x, ng=ng)
+    _, _, _, nz1, b1, _ = run_emu(emu, sp, PARAMS[1], "csc", x, flags=1, ng=ng)
+    _, _, _, nz2, b2, _ = run_emu(emu, sp, PARAMS[1], "csc", x, flags=2, ng=ng)
     assert np.array_equal(nz1, nz) and np.isnan(b1).all()
     assert np.array_equal(b2, b) and np.isnan(nz2).all()
 
 
+@pytest.mark.parametrize("ng", [0, 2], ids=["mma", "gath"])
 @pytest.mark.parametrize("nranks,nx,ny", [(2, 9, 8), (3, 5, 19)])
 @pytest.mark.parametrize("layout", ["csc", "csr"])
-def test_gather_kernel_row_blocks(emu, nranks, nx, ny, layout):
+def test_gather_kernel_row_blocks(emu, ng, nranks, nx, ny, layout):
     """Each rank assembles its owned cells only; lists of all nodes touching them (interface lines partial)."""
     prm = PARAMS[1]
     model = fe.CartesianModel((0, 1.5, 0, 1), (nx, ny))
@@ -175,7 +182,7 @@ def test_gather_kernel_row_blocks(emu, nranks, nx, ny, layout):
     forc = Oracle(full, **prm)
     for r in range(nranks):
         sp = fe.build_rank_spaces(model, cases.TURAN["V"], cases.TURAN["Ttags"], cases.TURAN["Texpr"], r, nranks)
-        _, ptr, idx, nz, b, g = run_emu(emu, sp, prm, layout, x, rows=sp.rows)
+        _, ptr, idx, nz, b, g = run_emu(emu, sp, prm, layout, x, rows=sp.rows, ng=ng)
         r0, r1, glo, ghi = sp.rows
         # reference: scatter of the owned cells through the local pattern
         rnz, rb = np.zeros(idx.size), np.zeros(full.n_total)

@@ -33,11 +33,11 @@ def _models():
 MODELS = dict(_models())
 
 
-def _check(gm, sp, prm, layout, path, x, floor=0.0):
+def _check(gm, sp, prm, layout, path, x, floor=0.0, kernel=0, xchunk=0):
     orc = Oracle(sp, **prm)
     optr, oidx = orc.pattern(layout)
     onz, ob = orc.assemble(x, layout)
-    h = gm.capi.Handle(sp, layout=layout, path=path)
+    h = gm.capi.Handle(sp, layout=layout, path=path, kernel=kernel, xchunk=xchunk)
     try:
         h.set_params(**prm)
         nnz = h.pattern()
@@ -123,20 +123,33 @@ def test_structured_path_matches_oracle(gm, gpu_lib, case, pi, layout):
     assert info["active_path"] == gm.capi.GM_PATH_CART
 
 
-@pytest.mark.parametrize("kernel", ["sweep", "gath_ng1"])
+@pytest.mark.parametrize("kernel", ["gath", "gath1", "sweep"])
 @pytest.mark.parametrize("case", [CART_CASES[1], CART_CASES[6], CART_CASES[9]], ids=lambda c: c[0])
 @pytest.mark.parametrize("layout", ["csc", "csr"])
-def test_structured_path_other_kernels(gm, gpu_lib, monkeypatch, kernel, case, layout):
-    """The first-generation sweep kernel (GM_CART_KERNEL=sweep) and the one-trio configuration of k_gath stay green."""
-    if kernel == "sweep":
-        monkeypatch.setenv("GM_CART_KERNEL", "sweep")
-    else:
-        monkeypatch.setenv("GM_GATH_NG", "1")
+def test_structured_path_other_kernels(gm, gpu_lib, kernel, case, layout):
+    """The older generations of the structured kernel (gm_desc.kernel: register gather k_gath with two / one trio,
+    first-generation sweep k_cart) stay selectable for A/B measurements and stay green."""
+    kid = {"gath": gm.capi.GM_KERNEL_GATH, "gath1": gm.capi.GM_KERNEL_GATH1, "sweep": gm.capi.GM_KERNEL_SWEEP}[kernel]
     _, nx, ny, bc = case
     sp = cases.cart(nx, ny, bc=bc, domain=(0, 1.5, 0, 1))
     x = fe.splitmix_iterate(sp.n_total, 1234)
     for pi in (0, 1):
-        _check(gm, sp, PARAMS[pi], layout, gm.capi.GM_PATH_CART, x)
+        _check(gm, sp, PARAMS[pi], layout, gm.capi.GM_PATH_CART, x, kernel=kid)
+
+
+@pytest.mark.parametrize("kernel", ["mma", "gath"])
+@pytest.mark.parametrize("xchunk", [32, 128, 256])
+@pytest.mark.parametrize("case", [CART_CASES[5], CART_CASES[6], CART_CASES[9]], ids=lambda c: c[0])
+def test_structured_path_chunk_lengths(gm, gpu_lib, kernel, xchunk, case):
+    """Every x-chunk length the library instantiates (gm_desc.xchunk; bench.py's grids pick 256, multi-GPU ranks 128)
+    against the oracle, with chunk seams inside the mesh where the mesh is long enough."""
+    kid = {"mma": gm.capi.GM_KERNEL_MMA, "gath": gm.capi.GM_KERNEL_GATH}[kernel]
+    if kernel == "gath" and xchunk == 32:
+        pytest.skip("k_gath is instantiated for 128 / 256 columns only")
+    _, nx, ny, bc = case
+    sp = cases.cart(nx, ny, bc=bc, domain=(0, 1.5, 0, 1))
+    x = fe.splitmix_iterate(sp.n_total, 1234)
+    _check(gm, sp, PARAMS[2], "csc", gm.capi.GM_PATH_CART, x, kernel=kid, xchunk=xchunk)
 
 
 def test_config2_256_matches_oracle(gm, gpu_lib):
