@@ -22,8 +22,8 @@
 //  * CTA = 4 main warps (one per SM sub-partition: the tensor pipe is per sub-partition) + 4 aux warps, 8 quad rows,
 //    2 CTAs per SM; setmaxnreg moves registers from the aux to the main warpgroup.  Main: tiles, state of column X+1,
 //    residual.  Aux: cp.async gathers of dof ids / iterate values / list bases of the coming columns, the constant P-block
-//    entries, TMA write-out (one cp.async.bulk per completed list, as k_gath).  One staging buffer: the write-out of column
-//    X-1 drains under the DMMA passes of column X; an mbarrier ("stage free") releases the first epilogue store.
+//    entries, write-out of the completed lists with 16-byte vector stores.  One staging buffer: the write-out of column
+//    X-1 runs under the first DMMA passes of column X; an mbarrier ("stage free") releases the first epilogue store.
 //
 // The file compiles for the device and -- with GM_EMU -- as host C++ under tests/emu/cuda_emu.h (tests/test_gath_emu.py).
 #pragma once
@@ -70,6 +70,7 @@ __device__ __forceinline__ void mm_mbar_wait(unsigned long long *bar, unsigned p
       "bra W_%=;\n"
       "D_%=: }" ::"r"(sa), "r"(parity) : "memory");
 }
+__device__ __forceinline__ void mm_syncwarp() { __syncwarp(); }
 template <int N> __device__ __forceinline__ void mm_reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void mm_reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 __device__ __forceinline__ double mm_mask(double v, uint32_t mw, uint32_t sign) {  // (v masked by mw) with the sign bit flipped by `sign`
@@ -90,10 +91,11 @@ struct MmSmem {
   double rBp[32];                      // pressure rows: w psi
   double tphi[4][9], tdx[4][9], tdy[4][9], tw[4], twpsi[4][3], tpsi[4][3];
   double UP[18][3];
-  unsigned long long mbar_free;        // "stage free": all TMA reads of the previous column's lists are done
+  unsigned long long mbar_free;        // "stage free": the write-out of the previous column has read its lists
   int32_t gd[4][MM_NR][30];            // dof ids of cell column c (c & 3)
   int32_t lg[4][MM_QH][16];            // dof id of each list of quad column X (0: no list / not assembled here)
   int32_t cls[4][MM_NR];
+  uint4 wd[MM_NAW * 32];               // write-out descriptors of the aux threads' lists
   uint32_t out[64];                    // MmOut of output t*8+n (A | bx<<8 | by<<16 | vmask<<24)
   int16_t slot[16];
   uint8_t par[4][MM_QH][8];            // parities of the list bases of quad column X (X & 3): [node type | 4 = P] bits k
@@ -327,35 +329,57 @@ __global__ void __launch_bounds__(MM_NT, 2) k_mma(MmArgs args) {
         stg0[rowq * GA_QSTRIDE + par + rk[rowq]] = own[rowq] ? pe_val : 0.0;
       }
     };
-    // (A7) write-out of quad column X: one TMA bulk copy per completed list
+    // (A7) write-out of quad column X: plain 16-byte vector stores, one aux warp per quad row and list.  (A TMA bulk copy per
+    //      list -- k_gath's way -- has a read-completion latency of several thousand cycles, profiles/r02_ubench_bulk_copy_rate.txt:
+    //      with ONE staging buffer the main warps would wait for it every column; a store has released its staging bytes as
+    //      soon as it has issued.)  Lists are staged at slot + (base & 1), so source and destination are 16-byte aligned together.
+    //      Aux thread t < 120 looks up list t = (quad row, list) -- base, length, parity --, stores its odd head / tail
+    //      element itself and leaves a descriptor for its warp; then the warp walks the 32 lists of its lanes four at a time:
+    //      an 8-lane group copies one list (at most 45 chunks: 6 rounds), 128 contiguous bytes per group and instruction.
     auto write_out = [&](int X) {
-      ga_fence_async();
-      for (int k = at; k < QH * 15; k += NAT) {
-        const int rowq = k / 15, li = k - rowq * 15;
-        if (rowq >= nqr) break;
-        if (s.lg[X & 3][rowq][li] <= 0) continue;
-        const long long base = s.lbase[X & 3][rowq][li];
-        const int len = (int)(s.lnext[X & 3][rowq][li] - base);
-        const int par = (int)(base & 1);
-        const double *src = s.stage + rowq * GA_QSTRIDE + s.slot[li] + par;  // element k of the list lives at src[k]
-        double *dst = a.nz + base;
-        int k0 = 0, n = len;
-        if (par) { dst[0] = src[0]; k0 = 1; n -= 1; }
-        if (n & 1) { dst[k0 + n - 1] = src[k0 + n - 1]; n -= 1; }
-        if (n > 0) ga_bulk_store(dst + k0, src + k0, n * 8);
+      uint4 d = uint4{0, 0, 0, 0};  // x: first chunk in the staging buffer (16-byte units), y: chunks, (z, w): address of the first chunk in nzval
+      if (at < QH * 15) {
+        const int rowq = at / 15, li = at - rowq * 15;
+        if (rowq < nqr && s.lg[X & 3][rowq][li] > 0) {
+          const long long base = s.lbase[X & 3][rowq][li];
+          const int len = (int)(s.lnext[X & 3][rowq][li] - base);
+          const int par = (int)(base & 1);
+          const double *src = s.stage + rowq * GA_QSTRIDE + s.slot[li] + par;  // element k of the list lives at src[k]
+          double *dst = a.nz + base;
+          if (par) dst[0] = src[0];
+          if ((len - par) & 1) dst[len - 1] = src[len - 1];
+          const unsigned long long ga = (unsigned long long)(dst + par);
+          d = uint4{(uint32_t)((rowq * GA_QSTRIDE + s.slot[li]) / 2 + par), (uint32_t)((len - par) >> 1), (uint32_t)ga, (uint32_t)(ga >> 32)};
+        }
       }
-      ga_bulk_commit();
+      s.wd[at] = d;
+      mm_syncwarp();
+      const double2 *st2 = reinterpret_cast<const double2 *>(s.stage);
+      const int sub = lane & 7;
+#pragma unroll 2
+      for (int it = 0; it < 8; ++it) {
+        const uint4 e = s.wd[(at & ~31) + 4 * it + (lane >> 3)];
+        double2 *d2 = reinterpret_cast<double2 *>(((unsigned long long)e.w << 32) | e.z);
+        const double2 *s2 = st2 + e.x;
+        double2 v[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+          if (sub + 8 * r < (int)e.y) v[r] = s2[sub + 8 * r];
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+          if (sub + 8 * r < (int)e.y) d2[sub + 8 * r] = v[r];
+      }
+      mm_syncwarp();
     };
 
     unsigned phase = 0;
     for (int X = X0 - 4; X < X1; ++X) {
       const bool live = X >= X0;
       if (live && X > X0 && jac) write_out(X - 1);
+      mm_mbar_arrive(&s.mbar_free);        // my stores of column X-1 have issued: their staging bytes are released
       issue_gd(X + 3);
       issue_val(X + 2);
       if (X + 1 >= X0 && X + 1 < X1) issue_lists(X + 1);
-      ga_bulk_wait_read();                 // my bulk copies have read the staging buffer
-      mm_mbar_arrive(&s.mbar_free);
       if (live && jac) {
         mm_mbar_wait(&s.mbar_free, phase);  // ... and everybody else's
         p_entries(X);
@@ -363,13 +387,9 @@ __global__ void __launch_bounds__(MM_NT, 2) k_mma(MmArgs args) {
       phase ^= 1;
       ga_cp_wait_all();
       if (X + 1 >= X0 && X + 1 < X1) lists_parity(X + 1);
-      ga_fence_async();
       ga_bar_step<NT>();  // lists of column X staged, state of X+1 ready, asynchronous copies landed
     }
-    if (jac) {  // last column of the chunk
-      write_out(X1 - 1);
-      ga_bulk_wait_read();
-    }
+    if (jac) write_out(X1 - 1);  // last column of the chunk
   } else {
 #ifndef GM_EMU
     mm_reg_inc<MM_REG_MAIN>();
@@ -381,6 +401,8 @@ __global__ void __launch_bounds__(MM_NT, 2) k_mma(MmArgs args) {
     const int g = lane >> 2, j = lane & 3;
     double Bt[2][8];      // per tile slot: reference-element products of B column g at point j
     uint32_t bmask[2];    // per tile slot: variant mask of B column g
+    int tile8[2];         // per tile slot: 8 * tile id
+    uint32_t tvar[2];     // per tile slot: variants of the tile (union over its columns)
     uint32_t selfast[2];  // per tile slot: epilogue selection of the two accumulator columns when both cell columns exist
     // epilogue selection of output `ow` (packed MmOut) for accumulator row g: which cell supplies the rank record
     // (any cell in the table that contains both nodes), how many owned cells are summed.
@@ -410,7 +432,7 @@ __global__ void __launch_bounds__(MM_NT, 2) k_mma(MmArgs args) {
 #pragma unroll
       for (int w = 0; w < 4; ++w)
         if (warp == w) t = mm_warp_tile(w, sl);
-      bmask[sl] = 0; selfast[sl] = 0;
+      bmask[sl] = 0; selfast[sl] = 0; tile8[sl] = 8 * t; tvar[sl] = 0;
 #pragma unroll
       for (int k = 0; k < 8; ++k) Bt[sl][k] = 0.0;
       if (t < 0) continue;
@@ -424,23 +446,28 @@ __global__ void __launch_bounds__(MM_NT, 2) k_mma(MmArgs args) {
       Bt[sl][MB_PS] = xi * yj + yi * xj;
       Bt[sl][MB_TM] = tb.TM[j]; Bt[sl][MB_EX] = tb.TP[j] * xj; Bt[sl][MB_EY] = tb.TP[j] * yj;
       bmask[sl] = ob >> 24;
+#pragma unroll
+      for (int tt = 0; tt < 8; ++tt)
+        if (t == tt) tvar[sl] = (uint32_t)mm_tvar(tt);
       selfast[sl] = select(s.out[t * 8 + 2 * j], true, true) | (select(s.out[t * 8 + 2 * j + 1], true, true) << 16);
     }
     int xm3 = (((X0 - 4) % 3) + 3) % 3;
     unsigned phase = 0;
     bool stage_ok = false;  // this step's "stage free" wait is done
 
-    // ---- one accumulator tile of quad column X (tile T in slot SL of this warp)
-    auto tile = [&](auto TT, auto SS, int X) {
-      constexpr int T = decltype(TT)::value, SL = decltype(SS)::value;
-      constexpr int TV = mm_tvar(T);
-      constexpr bool PURE = mm_tpure(T) != 0;
+    // ---- one accumulator tile of quad column X (the tile in slot SL of this warp).  The variant loop is a run-time loop
+    //      and all four main warps run the same code (tile id, variant set and column mask are per-warp registers): the
+    //      straight-line version (every tile x variant unrolled: 130 KB of SASS) lost 20 % of the issue slots to instruction fetch.
+    auto tile = [&](auto SS, int X) {
+      constexpr int SL = decltype(SS)::value;
+      const int T8 = tile8[SL];  // 8 * tile id
+      const uint32_t tv = tvar[SL];
       const bool okL = X > 0, okR = X < a.nx;
       // rank records of my two accumulator columns (issued first: they are needed in the epilogue only)
       uint32_t sel[2];
       uint4 rec[2];
       {
-        const uint32_t sf = (okL && okR) ? selfast[SL] : (select(s.out[T * 8 + 2 * j], okL, okR) | (select(s.out[T * 8 + 2 * j + 1], okL, okR) << 16));
+        const uint32_t sf = (okL && okR) ? selfast[SL] : (select(s.out[T8 + 2 * j], okL, okR) | (select(s.out[T8 + 2 * j + 1], okL, okR) << 16));
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           sel[c] = (sf >> (16 * c)) & 0xFFFFu;
@@ -452,14 +479,14 @@ __global__ void __launch_bounds__(MM_NT, 2) k_mma(MmArgs args) {
         }
       }
       double v00[2] = {0, 0}, v11[2] = {0, 0}, v01[2] = {0, 0}, v10[2] = {0, 0}, ee[2] = {0, 0}, tu0[2] = {0, 0}, tu1[2] = {0, 0};
-#pragma unroll
+#pragma unroll 1
       for (int m = 0; m < 4; ++m) {
-        if (!((TV >> m) & 1)) continue;
+        if (!((tv >> m) & 1)) continue;
         const int mx = m & 1, my = m >> 1;
         if (!(mx ? okL : okR)) continue;
         const double *P = s.st[mx ? (xm3 == 0 ? 2 : xm3 - 1) : xm3] + (g + 1 - my) * 4 + (j ^ m);
-        const uint32_t mw = PURE ? 0xFFFFFFFFu : (((bmask[SL] >> m) & 1) ? 0xFFFFFFFFu : 0u);
-        const uint32_t sxy = (m == 1 || m == 2) ? 0x80000000u : 0u, sx = mx ? 0x80000000u : 0u, sy = my ? 0x80000000u : 0u;
+        const uint32_t mw = ((bmask[SL] >> m) & 1) ? 0xFFFFFFFFu : 0u;  // my B column takes part in this variant
+        const uint32_t sxy = (uint32_t)((m ^ (m >> 1)) & 1) << 31, sx = (uint32_t)mx << 31, sy = (uint32_t)my << 31;
         const double bPXX = mm_mask(Bt[SL][MB_PXX], mw, 0), bPYY = mm_mask(Bt[SL][MB_PYY], mw, 0), bTM = mm_mask(Bt[SL][MB_TM], mw, 0);
         const double bPXY = mm_mask(Bt[SL][MB_PXY], mw, sxy), bPYX = mm_mask(Bt[SL][MB_PYX], mw, sxy), bPS = mm_mask(Bt[SL][MB_PS], mw, sxy);
         const double bEX = mm_mask(Bt[SL][MB_EX], mw, sx), bEY = mm_mask(Bt[SL][MB_EY], mw, sy);
@@ -488,15 +515,15 @@ __global__ void __launch_bounds__(MM_NT, 2) k_mma(MmArgs args) {
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         if (!(sel[c] >> 15)) continue;
-        const uint32_t ow = s.out[T * 8 + 2 * j + c];
+        const uint32_t ow = s.out[T8 + 2 * j + c];
         const int A = ow & 255;
         const uint32_t pm = s.par[X & 3][g][A];
         const int slot0 = A == 0 ? 0 : (A == 1 ? 258 : (A == 2 ? 414 : 570)), slen = A == 0 ? 90 : (A == 3 ? 34 : 54);
         double *b0 = q0 + slot0 + (pm & 1), *b1 = q0 + slot0 + slen + ((pm >> 1) & 1), *b2 = q0 + slot0 + 2 * slen + ((pm >> 2) & 1);
         const double cn = (double)((sel[c] >> 12) & 7);
-        const double mb = cn * s.ek[T * 8 + 2 * j + c][1];
+        const double mb = cn * s.ek[T8 + 2 * j + c][1];
         const double ut0 = -a.RaPr * a.gx * mb, ut1 = -a.RaPr * a.gy * mb;
-        const double e = ee[c], tt = fma(cn, s.ek[T * 8 + 2 * j + c][0], e);
+        const double e = ee[c], tt = fma(cn, s.ek[T8 + 2 * j + c][0], e);
         const double w00 = v00[c] + e, w11 = v11[c] + e;
         double e00, e01, e02, e10, e11, e12, e20, e21, e22;  // [list k][minor dof l]
         if (CSR) { e00 = w00; e01 = v01[c]; e02 = ut0; e10 = v10[c]; e11 = w11; e12 = ut1; e20 = tu0[c]; e21 = tu1[c]; e22 = tt; }
@@ -606,25 +633,14 @@ __global__ void __launch_bounds__(MM_NT, 2) k_mma(MmArgs args) {
     for (int X = X0 - 4; X < X1; ++X) {
       const bool live = X >= X0;
       stage_ok = false;
-      if (live && jac) {
-        if (warp == 0) {
-          tile(integral_constant<int, mm_warp_tile(0, 0)>{}, integral_constant<int, 0>{}, X);
-          tile(integral_constant<int, mm_warp_tile(0, 1)>{}, integral_constant<int, 1>{}, X);
-        } else if (warp == 1) {
-          tile(integral_constant<int, mm_warp_tile(1, 0)>{}, integral_constant<int, 0>{}, X);
-          tile(integral_constant<int, mm_warp_tile(1, 1)>{}, integral_constant<int, 1>{}, X);
-        } else if (warp == 2) {
-          tile(integral_constant<int, mm_warp_tile(2, 0)>{}, integral_constant<int, 0>{}, X);
-          tile(integral_constant<int, mm_warp_tile(2, 1)>{}, integral_constant<int, 1>{}, X);
-        } else {
-          tile(integral_constant<int, mm_warp_tile(3, 0)>{}, integral_constant<int, 0>{}, X);
-          tile(integral_constant<int, mm_warp_tile(3, 1)>{}, integral_constant<int, 1>{}, X);
-        }
-      }
+      // (the tasks that do not touch the staging buffer come first: the write-out of column X-1 is still reading it)
       if (warp == MM_WARP_RESIDUAL && live && res) residual_task(X);
       if (warp == MM_WARP_STATE) state_task(X + 1, xm3 == 2 ? 0 : xm3 + 1);
+      if (live && jac) {
+        tile(integral_constant<int, 0>{}, X);
+        tile(integral_constant<int, 1>{}, X);
+      }
       phase ^= 1;
-      ga_fence_async();  // staged entries -> visible to the TMA (async proxy) reads of the next step
       xm3 = xm3 == 2 ? 0 : xm3 + 1;
       ga_bar_step<NT>();
     }

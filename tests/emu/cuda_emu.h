@@ -86,6 +86,7 @@ static inline void mm_mbar_arrive(unsigned long long *bar) {
 static inline void mm_mbar_wait(unsigned long long *bar, unsigned parity) {
   while ((unsigned)(__atomic_load_n(bar, __ATOMIC_ACQUIRE) >> 32) == parity) sched_yield();
 }
+static inline void mm_syncwarp() { pthread_barrier_wait(&g_emu_bar_warp[threadIdx.x >> 5]); }
 static inline double mm_mask(double v, uint32_t mw, uint32_t sign) {
   uint64_t b;
   memcpy(&b, &v, 8);
