@@ -363,6 +363,7 @@ template <bool CSR, bool NEWT, int XCH>
 static int gm_mma_launch2(gm_handle *h, const CartArgs &a, int nstrips) {
   const size_t sm = sizeof(MmSmem);
   GM_CUDA(cudaFuncSetAttribute(k_mma<CSR, NEWT, XCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));  // (per device: set on every launch)
+  GM_CUDA(cudaFuncSetAttribute(k_mma<CSR, NEWT, XCH>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));  // two CTAs per SM
   MmArgs ma;
   ma.a = a;
   memcpy(ma.out, MM_OUT, sizeof ma.out);

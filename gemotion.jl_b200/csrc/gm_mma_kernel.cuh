@@ -38,8 +38,8 @@
 #define MM_NMW 4                     // main warps
 #define MM_NAW 4                     // aux warps
 #define MM_NT ((MM_NMW + MM_NAW) * 32)
-#define MM_REG_MAIN 168              // setmaxnreg targets: (168 + 88) * 128 threads = 32768 = half the register file (2 CTAs / SM)
-#define MM_REG_AUX 88
+#define MM_REG_MAIN 160              // setmaxnreg targets: main + aux = 256 (x 128 threads = half the register file: 2 CTAs / SM)
+#define MM_REG_AUX 96
 
 enum { PL_A0, PL_A1, PL_BM, PL_AA, PL_C1, PL_C2, PL_G00, PL_G11, PL_G01, PL_G10, PL_DT0, PL_DT1, PL_U0, PL_U1,
        PL_F0X, PL_F0Y, PL_F1Y, PL_F0C, PL_F1C, PL_FTC, MM_NPL };
@@ -95,7 +95,8 @@ struct MmSmem {
   int32_t gd[4][MM_NR][30];            // dof ids of cell column c (c & 3)
   int32_t lg[4][MM_QH][16];            // dof id of each list of quad column X (0: no list / not assembled here)
   int32_t cls[4][MM_NR];
-  uint4 wd[MM_NAW * 32];               // write-out descriptors of the aux threads' lists
+  uint4 wd[2][MM_QH * 15 + 8];         // write-out descriptors of the lists of quad column X (X & 1), see list_desc
+  uint4 prec[81];                      // rank records (a.ptab) of the strip's reference class: most cells belong to it
   uint32_t out[64];                    // MmOut of output t*8+n (A | bx<<8 | by<<16 | vmask<<24)
   int16_t slot[16];
   uint8_t par[4][MM_QH][8];            // parities of the list bases of quad column X (X & 3): [node type | 4 = P] bits k
@@ -179,6 +180,9 @@ __global__ void __launch_bounds__(MM_NT, 2) k_mma(MmArgs args) {
       s.rBp[tid] = n < 3 ? cc.wpsi[q][n] : 0.0;
     }
   }
+  // reference rank class of this CTA (the class of an interior cell of the strip): its records are served from shared memory
+  const int cls0 = a.cls[(int64_t)min(max(Yc0 + 3, 0), a.ny - 1) * a.nx + min(X0 + 3, a.nx - 1)];
+  if (tid < 81) s.prec[tid] = GA_LDG(reinterpret_cast<const uint4 *>(a.ptab) + ((int64_t)cls0 * 81 + tid));
   if (tid == 0) {
     const int16_t sl[16] = {0, 90, 180, 258, 312, 366, 414, 468, 522, 570, 604, 638, 668, 688, 708, 728};
     for (int k = 0; k < 16; ++k) s.slot[k] = sl[k];
@@ -285,6 +289,21 @@ __global__ void __launch_bounds__(MM_NT, 2) k_mma(MmArgs args) {
       const long long *lb = &s.lbase[c & 3][rowq][grp * 3];
       s.par[c & 3][rowq][grp] = (uint8_t)((lb[0] & 1) | ((lb[1] & 1) << 1) | ((lb[2] & 1) << 2));
     };
+    // write-out descriptor of list `at` of quad column c (one step after its base / end have landed, off the critical path)
+    auto list_desc = [&](int c) {
+      if (at >= QH * 15) return;
+      const int rowq = at / 15, li = at - rowq * 15;
+      uint4 d = uint4{0, 0, 0, 0};
+      if (s.lg[c & 3][rowq][li] > 0) {
+        const long long base = s.lbase[c & 3][rowq][li];
+        const int len = (int)(s.lnext[c & 3][rowq][li] - base), par = (int)(base & 1);
+        const unsigned long long off = (unsigned long long)(base + par);  // first 16-byte chunk in nzval (doubles)
+        // x: first chunk in the staging buffer (16-byte units); y: chunks | odd head << 8 | odd tail << 9; (z, w): off
+        d = uint4{(uint32_t)((rowq * GA_QSTRIDE + s.slot[li]) / 2 + par), (uint32_t)((len - par) >> 1) | ((uint32_t)par << 8) | ((uint32_t)((len - par) & 1) << 9),
+                  (uint32_t)off, (uint32_t)(off >> 32)};
+      }
+      s.wd[c & 1][at] = d;
+    };
     // (A5) constant P-block entries of quad column X -> staged lists.  Aux thread e < 108 owns entry type e
     int pe_li = 0, pe_rk = 0, pe_dx = 0, pe_dy = 0;
     double pe_val = 0.0;
@@ -305,7 +324,7 @@ __global__ void __launch_bounds__(MM_NT, 2) k_mma(MmArgs args) {
         pe_val = (CSR ? -1.0 : 1.0) * s.UP[ud][p];
       }
     }
-    const int pe_cls0 = pe_on ? a.cls[(int64_t)min(max(Yc0 + 3, 0), a.ny - 1) * a.nx + min(X0 + 3, a.nx - 1)] : 0;
+    const int pe_cls0 = cls0;
     const int pe_rk0 = pe_on ? (int)GA_LDG(a.ctab + (int64_t)pe_cls0 * 900 + pe_rk) : 0xFF;
     auto p_entries = [&](int X) {
       if (!pe_on) return;
@@ -333,43 +352,35 @@ __global__ void __launch_bounds__(MM_NT, 2) k_mma(MmArgs args) {
     //      list -- k_gath's way -- has a read-completion latency of several thousand cycles, profiles/r02_ubench_bulk_copy_rate.txt:
     //      with ONE staging buffer the main warps would wait for it every column; a store has released its staging bytes as
     //      soon as it has issued.)  Lists are staged at slot + (base & 1), so source and destination are 16-byte aligned together.
-    //      Aux thread t < 120 looks up list t = (quad row, list) -- base, length, parity --, stores its odd head / tail
-    //      element itself and leaves a descriptor for its warp; then the warp walks the 32 lists of its lanes four at a time:
-    //      an 8-lane group copies one list (at most 45 chunks: 6 rounds), 128 contiguous bytes per group and instruction.
+    //      Descriptors (staging offset, chunks, offset in nzval) are left by list_desc; a warp walks 30 lists four at a
+    //      time: an 8-lane group copies one list (at most 45 chunks: 6 rounds), 128 contiguous bytes per group and instruction.
+    const int awarp = warp - MM_NMW;
     auto write_out = [&](int X) {
-      uint4 d = uint4{0, 0, 0, 0};  // x: first chunk in the staging buffer (16-byte units), y: chunks, (z, w): address of the first chunk in nzval
-      if (at < QH * 15) {
-        const int rowq = at / 15, li = at - rowq * 15;
-        if (rowq < nqr && s.lg[X & 3][rowq][li] > 0) {
-          const long long base = s.lbase[X & 3][rowq][li];
-          const int len = (int)(s.lnext[X & 3][rowq][li] - base);
-          const int par = (int)(base & 1);
-          const double *src = s.stage + rowq * GA_QSTRIDE + s.slot[li] + par;  // element k of the list lives at src[k]
-          double *dst = a.nz + base;
-          if (par) dst[0] = src[0];
-          if ((len - par) & 1) dst[len - 1] = src[len - 1];
-          const unsigned long long ga = (unsigned long long)(dst + par);
-          d = uint4{(uint32_t)((rowq * GA_QSTRIDE + s.slot[li]) / 2 + par), (uint32_t)((len - par) >> 1), (uint32_t)ga, (uint32_t)(ga >> 32)};
-        }
-      }
-      s.wd[at] = d;
-      mm_syncwarp();
       const double2 *st2 = reinterpret_cast<const double2 *>(s.stage);
       const int sub = lane & 7;
+      const uint4 *wd = &s.wd[X & 1][awarp * 32 + (lane >> 3)];
 #pragma unroll 2
       for (int it = 0; it < 8; ++it) {
-        const uint4 e = s.wd[(at & ~31) + 4 * it + (lane >> 3)];
-        double2 *d2 = reinterpret_cast<double2 *>(((unsigned long long)e.w << 32) | e.z);
+        if (awarp * 32 + 4 * it >= QH * 15) break;  // (120 lists: the last warp has 24)
+        const uint4 e = wd[4 * it];
+        const int nch = (int)(e.y & 255);
+        double *gp = a.nz + (((unsigned long long)e.w << 32) | e.z);
+        double2 *d2 = reinterpret_cast<double2 *>(gp);
         const double2 *s2 = st2 + e.x;
         double2 v[6];
 #pragma unroll
         for (int r = 0; r < 6; ++r)
-          if (sub + 8 * r < (int)e.y) v[r] = s2[sub + 8 * r];
+          if (sub + 8 * r < nch) v[r] = s2[sub + 8 * r];
+        const bool head = sub == 0 && ((e.y >> 8) & 1), tail = sub == 1 && ((e.y >> 9) & 1);
+        double vh = 0.0;
+        if (head) vh = reinterpret_cast<const double *>(s2)[-1];
+        if (tail) vh = reinterpret_cast<const double *>(s2)[2 * nch];
 #pragma unroll
         for (int r = 0; r < 6; ++r)
-          if (sub + 8 * r < (int)e.y) d2[sub + 8 * r] = v[r];
+          if (sub + 8 * r < nch) d2[sub + 8 * r] = v[r];
+        if (head) gp[-1] = vh;
+        if (tail) gp[2 * nch] = vh;
       }
-      mm_syncwarp();
     };
 
     unsigned phase = 0;
@@ -377,6 +388,7 @@ __global__ void __launch_bounds__(MM_NT, 2) k_mma(MmArgs args) {
       const bool live = X >= X0;
       if (live && X > X0 && jac) write_out(X - 1);
       mm_mbar_arrive(&s.mbar_free);        // my stores of column X-1 have issued: their staging bytes are released
+      if (live && jac) list_desc(X);
       issue_gd(X + 3);
       issue_val(X + 2);
       if (X + 1 >= X0 && X + 1 < X1) issue_lists(X + 1);
@@ -474,7 +486,8 @@ __global__ void __launch_bounds__(MM_NT, 2) k_mma(MmArgs args) {
           rec[c] = uint4{0, 0, 0, 0};
           if (sel[c] >> 15) {
             const int cx = X - (int)((sel[c] >> 11) & 1);
-            rec[c] = GA_LDG(reinterpret_cast<const uint4 *>(a.ptab) + ((int64_t)s.cls[cx & 3][(sel[c] >> 7) & 15] * 81 + (sel[c] & 127)));
+            const int cl = s.cls[cx & 3][(sel[c] >> 7) & 15];
+            rec[c] = cl == cls0 ? s.prec[sel[c] & 127] : GA_LDG(reinterpret_cast<const uint4 *>(a.ptab) + ((int64_t)cl * 81 + (sel[c] & 127)));
           }
         }
       }
@@ -490,23 +503,27 @@ __global__ void __launch_bounds__(MM_NT, 2) k_mma(MmArgs args) {
         const double bPXX = mm_mask(Bt[SL][MB_PXX], mw, 0), bPYY = mm_mask(Bt[SL][MB_PYY], mw, 0), bTM = mm_mask(Bt[SL][MB_TM], mw, 0);
         const double bPXY = mm_mask(Bt[SL][MB_PXY], mw, sxy), bPYX = mm_mask(Bt[SL][MB_PYX], mw, sxy), bPS = mm_mask(Bt[SL][MB_PS], mw, sxy);
         const double bEX = mm_mask(Bt[SL][MB_EX], mw, sx), bEY = mm_mask(Bt[SL][MB_EY], mw, sy);
-        double av;
-        av = P[PL_A0 * MM_PST]; mm_dmma(v00, av, bPXX);
-        av = P[PL_A1 * MM_PST]; mm_dmma(v11, av, bPYY);
-        av = P[PL_BM * MM_PST]; mm_dmma(v00, av, bPYY); mm_dmma(v11, av, bPXX); mm_dmma(v01, av, bPYX); mm_dmma(v10, av, bPXY);
+        // all coefficient planes of the pass first (the loads are independent of everything before them)
+        double pa[14];
+#pragma unroll
+        for (int k = 0; k < 14; ++k)
+          if (!(NEWT && (k == PL_AA || k == PL_C1 || k == PL_C2))) pa[k] = P[k * MM_PST];
+        mm_dmma(v00, pa[PL_A0], bPXX);
+        mm_dmma(v11, pa[PL_A1], bPYY);
+        mm_dmma(v01, pa[PL_BM], bPYX); mm_dmma(v10, pa[PL_BM], bPXY); mm_dmma(v00, pa[PL_BM], bPYY); mm_dmma(v11, pa[PL_BM], bPXX);
+        mm_dmma(tu0, pa[PL_DT0], bTM);
+        mm_dmma(tu1, pa[PL_DT1], bTM);
+        mm_dmma(ee, pa[PL_U0], bEX);      // w phi_i (u . grad phi_j)
+        mm_dmma(v01, pa[PL_G10], bTM);    // (a=0,b=1): + w phi phi G[1][0]
+        mm_dmma(v10, pa[PL_G01], bTM);    // (a=1,b=0): + w phi phi G[0][1]
+        mm_dmma(v00, pa[PL_G00], bTM);
+        mm_dmma(v11, pa[PL_G11], bTM);
+        mm_dmma(ee, pa[PL_U1], bEY);
         if (!NEWT) {
-          av = P[PL_AA * MM_PST]; mm_dmma(v01, av, bPXY); mm_dmma(v10, av, bPYX);
-          av = P[PL_C1 * MM_PST]; mm_dmma(v00, av, bPS); mm_dmma(v01, av, bPXX); mm_dmma(v10, av, bPXX);
-          av = P[PL_C2 * MM_PST]; mm_dmma(v11, av, bPS); mm_dmma(v01, av, bPYY); mm_dmma(v10, av, bPYY);
+          mm_dmma(v01, pa[PL_AA], bPXY); mm_dmma(v10, pa[PL_AA], bPYX);
+          mm_dmma(v00, pa[PL_C1], bPS); mm_dmma(v01, pa[PL_C1], bPXX); mm_dmma(v10, pa[PL_C1], bPXX);
+          mm_dmma(v11, pa[PL_C2], bPS); mm_dmma(v01, pa[PL_C2], bPYY); mm_dmma(v10, pa[PL_C2], bPYY);
         }
-        av = P[PL_G00 * MM_PST]; mm_dmma(v00, av, bTM);
-        av = P[PL_G11 * MM_PST]; mm_dmma(v11, av, bTM);
-        av = P[PL_G10 * MM_PST]; mm_dmma(v01, av, bTM);   // (a=0,b=1): + w phi phi G[1][0]
-        av = P[PL_G01 * MM_PST]; mm_dmma(v10, av, bTM);   // (a=1,b=0): + w phi phi G[0][1]
-        av = P[PL_DT0 * MM_PST]; mm_dmma(tu0, av, bTM);
-        av = P[PL_DT1 * MM_PST]; mm_dmma(tu1, av, bTM);
-        av = P[PL_U0 * MM_PST]; mm_dmma(ee, av, bEX);     // w phi_i (u . grad phi_j)
-        av = P[PL_U1 * MM_PST]; mm_dmma(ee, av, bEY);
       }
       // ---- epilogue: nine entries per output -> staged lists (positions from the rank record; entries without a
       //      position go to the trash element of their slot)
