@@ -369,6 +369,19 @@ static int gm_mma_launch2(gm_handle *h, const CartArgs &a, int nstrips) {
   memcpy(ma.out, MM_OUT, sizeof ma.out);
   dim3 grid((a.nx + 1 + XCH - 1) / XCH, nstrips);
   k_mma<CSR, NEWT, XCH><<<grid, MM_NT, sm, h->stream>>>(ma);
+#ifdef MM_PROF
+  {  // development build: cycles per warp and phase of the middle CTA (main: 0 write-out, 1 residual / state, 2 passes, 3 stage wait,
+     // 5 / 6 epilogues of slot 0 / 1, 7 barrier; aux: 0 write-out, 1 gathers, 2 P entries, 3 cp.async wait, 4 parities, 7 barrier)
+    long long hp[8][8];
+    cudaStreamSynchronize(h->stream);
+    cudaMemcpyFromSymbol(hp, mm_prof, sizeof hp);
+    for (int w = 0; w < 8; ++w) {
+      fprintf(stderr, "mm_prof warp %d:", w);
+      for (int k = 0; k < 8; ++k) fprintf(stderr, " %9lld", hp[w][k]);
+      fprintf(stderr, "\n");
+    }
+  }
+#endif
   return GM_OK;
 }
 template <bool CSR, bool NEWT>

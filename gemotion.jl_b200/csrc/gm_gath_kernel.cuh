@@ -88,6 +88,8 @@ __device__ __forceinline__ void ga_cp_wait_all() {
   asm volatile("cp.async.commit_group;" ::: "memory");
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
+__device__ __forceinline__ void ga_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void ga_cp_wait_prev() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }  // all but the newest group
 __device__ __forceinline__ void ga_bulk_store(double *gdst, const double *ssrc, int bytes) {
   const uint32_t sa = (uint32_t)__cvta_generic_to_shared(ssrc);
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(sa), "r"(bytes) : "memory");

@@ -38,6 +38,7 @@
 #define MM_NMW 4                     // main warps
 #define MM_NAW 4                     // aux warps
 #define MM_NT ((MM_NMW + MM_NAW) * 32)
+#define MM_WARM 6                    // warm-up steps of the column pipeline
 #define MM_REG_MAIN 160              // setmaxnreg targets: main + aux = 256 (x 128 threads = half the register file: 2 CTAs / SM)
 #define MM_REG_AUX 96
 
@@ -78,6 +79,14 @@ __device__ __forceinline__ double mm_mask(double v, uint32_t mw, uint32_t sign) 
 }
 #endif
 
+// ---- optional phase timing (development builds only: make EXTRA=-DMM_PROF): cycles per warp and phase of one CTA
+#if defined(MM_PROF) && !defined(GM_EMU)
+__device__ long long mm_prof[8][8];
+#define MM_T(k) do { if (prof_on) { const long long t__ = clock64(); pacc[k] += t__ - ptl; ptl = t__; } } while (0)
+#else
+#define MM_T(k) do { } while (0)
+#endif
+
 struct MmSmem {
   double stage[MM_QH * GA_QSTRIDE];    // staged lists of the quad column being assembled
   double st[3][MM_NPL * MM_PST];       // state ring (cell column mod 3), plane-major
@@ -92,9 +101,10 @@ struct MmSmem {
   double tphi[4][9], tdx[4][9], tdy[4][9], tw[4], twpsi[4][3], tpsi[4][3];
   double UP[18][3];
   unsigned long long mbar_free;        // "stage free": the write-out of the previous column has read its lists
-  int32_t gd[4][MM_NR][30];            // dof ids of cell column c (c & 3)
+  int32_t gd[8][MM_NR][30];            // dof ids of cell column c (c & 7)
   int32_t lg[4][MM_QH][16];            // dof id of each list of quad column X (0: no list / not assembled here)
-  int32_t cls[4][MM_NR];
+  int32_t cls[8][MM_NR];               // rank class of the cells of column c (c & 7)
+  int32_t pdiff[4];                    // quad column X (X & 3): its constant P entries differ from those of column X-1
   uint4 wd[2][MM_QH * 15 + 8];         // write-out descriptors of the lists of quad column X (X & 1), see list_desc
   uint4 prec[81];                      // rank records (a.ptab) of the strip's reference class: most cells belong to it
   uint32_t out[64];                    // MmOut of output t*8+n (A | bx<<8 | by<<16 | vmask<<24)
@@ -198,6 +208,60 @@ __global__ void __launch_bounds__(MM_NT, 2) k_mma(MmArgs args) {
   }
   __syncthreads();
 
+  // ---- write-out of quad column X (the four aux warps, two quad rows each -- 16 lanes per row --, right after the step
+  //      barrier): plain 16-byte vector stores.  (A TMA bulk copy per list -- k_gath's way -- has a read-completion latency
+  //      of several thousand cycles, profiles/r02_ubench_bulk_copy_rate.txt: with ONE staging buffer the main warps would
+  //      wait for it every column; a store has released its staging bytes as soon as it has issued.)  Lists are staged at
+  //      slot + (base & 1), so source and destination are 16-byte aligned together.  Descriptors (staging offset, chunks,
+  //      offset in nzval) are left by list_desc.  The 15 lists go in five groups of three with all descriptor loads, then all
+  //      data loads, then all stores of a group issued back to back (one list after the other is a chain of three
+  //      shared-memory latencies per list: 3,000 cycles per column); lanes 0 / 1 of a half warp store the odd head / tail.
+  auto write_out = [&](int X) {
+    const int rowq = 2 * (warp - MM_NMW) + (lane >> 4), sub = lane & 15;
+    const double2 *st2 = reinterpret_cast<const double2 *>(s.stage);
+    const uint4 *wd = &s.wd[X & 1][rowq * 15];
+    auto group = [&](auto L0, auto RR) {
+      constexpr int li0 = decltype(L0)::value, R = decltype(RR)::value;  // first list of the group, rounds of 16 chunks per list
+      uint4 e[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) e[k] = wd[li0 + k];
+      double2 v[3][R];
+      double vh[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int nch = (int)(e[k].y & 255);
+        const double2 *s2 = st2 + e[k].x;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          v[k][r] = make_double2(0, 0);
+          if (sub + 16 * r < nch) v[k][r] = s2[sub + 16 * r];
+        }
+        vh[k] = 0.0;
+        if (sub < 2 && ((e[k].y >> (8 + sub)) & 1)) vh[k] = reinterpret_cast<const double *>(s2)[sub ? 2 * nch : -1];
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int nch = (int)(e[k].y & 255);
+        double *gp = a.nz + (((unsigned long long)e[k].w << 32) | e[k].z);
+        double2 *d2 = reinterpret_cast<double2 *>(gp);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          if (sub + 16 * r < nch) d2[sub + 16 * r] = v[k][r];
+        if (sub < 2 && ((e[k].y >> (8 + sub)) & 1)) gp[sub ? 2 * nch : -1] = vh[k];
+      }
+    };
+    using std::integral_constant;
+    group(integral_constant<int, 0>{}, integral_constant<int, 3>{});   // vertex lists: at most 45 chunks
+    group(integral_constant<int, 3>{}, integral_constant<int, 2>{});   // bottom-edge lists: at most 27
+    group(integral_constant<int, 6>{}, integral_constant<int, 2>{});   // left-edge lists
+    group(integral_constant<int, 9>{}, integral_constant<int, 1>{});   // centre lists: at most 15
+    group(integral_constant<int, 12>{}, integral_constant<int, 1>{});  // pressure lists: at most 9
+  };
+
+#if defined(MM_PROF) && !defined(GM_EMU)
+  const bool prof_on = lane == 0 && blockIdx.x == gridDim.x / 2 && blockIdx.y == gridDim.y / 2;
+  long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ptl = clock64();
+#endif
   // =====================================================================================
   // column sweep.  Step X (main: quad column X): aux prepares dof ids of X+3, values of X+2, list records of X+1 and
   // writes out column X-1; main computes the state of X+1 after its tiles.  Four warm-up steps fill the pipeline.
@@ -208,6 +272,7 @@ __global__ void __launch_bounds__(MM_NT, 2) k_mma(MmArgs args) {
 #endif
     // (A1/A2) every aux thread owns up to three fixed (state row, local dof) items of a cell column
     static_assert(NR * 30 <= 3 * NAT, "three load items per aux thread");
+    static_assert(2 * MM_NAW == MM_QH, "write_out: two quad rows per aux warp");
     int li_src[3], li_dst[3];   // item index rr*30 + l in gd (-1: none), rr*MM_VST + l in val
     int64_t li_goff[3];         // offset of the item in gdofs for column 0
 #pragma unroll
@@ -220,7 +285,7 @@ __global__ void __launch_bounds__(MM_NT, 2) k_mma(MmArgs args) {
     }
     auto issue_gd = [&](int c) {
       if (!col_ok(c)) return;
-      int32_t *dst = &s.gd[c & 3][0][0];
+      int32_t *dst = &s.gd[c & 7][0][0];
       const int32_t *src = a.gdofs + (int64_t)c * 30;
 #pragma unroll
       for (int j = 0; j < 3; ++j)
@@ -228,7 +293,7 @@ __global__ void __launch_bounds__(MM_NT, 2) k_mma(MmArgs args) {
     };
     auto issue_val = [&](int c) {
       if (!col_ok(c)) return;
-      const int32_t *gdc = &s.gd[c & 3][0][0];
+      const int32_t *gdc = &s.gd[c & 7][0][0];
       double *dst = &s.val[c & 3][0][0];
 #pragma unroll
       for (int j = 0; j < 3; ++j)
@@ -236,18 +301,19 @@ __global__ void __launch_bounds__(MM_NT, 2) k_mma(MmArgs args) {
           const int32_t d = gdc[li_src[j]];
           ga_cp8(dst + li_dst[j], d > 0 ? a.x + (d - 1) : a.dvals + (-d - 1));
         }
-      for (int k = at; k < NR * 4; k += NAT) {
+      for (int k = at - 32; k >= 0 && k < NR * 4; k += NAT) {  // (warp 5 and a few threads of warp 6)
         const int rr = k >> 2, q = k & 3;
         if (!row_in_table(rr)) continue;
         const int64_t cell = (int64_t)(Yc0 + rr) * a.nx + c;
         if (!NEWT) ga_cp16(&s.visc[c & 3][rr][q][0], a.visc + (cell * 4 + q) * 2);
-        if (q == 0) ga_cp4(&s.cls[c & 3][rr], a.cls + cell);
+        if (q == 0) ga_cp4(&s.cls[c & 7][rr], a.cls + cell);
       }
     };
     // (A4) list records of quad column c: one thread per (quad row, node type | P lists) = three lists
+    const int lt = at - 64;  // list-record tasks live on warps 6 and 7 (the value gathers keep warps 4 and 5 busier)
     auto issue_lists = [&](int c) {
-      if (at >= QH * 5) return;
-      const int rowq = at / 5, grp = at - rowq * 5;
+      if (lt < 0 || lt >= QH * 5) return;
+      const int rowq = lt / 5, grp = lt - rowq * 5;
       int32_t g[3] = {0, 0, 0};
       bool active = false;
       if (rowq < nqr) {
@@ -260,13 +326,13 @@ __global__ void __launch_bounds__(MM_NT, 2) k_mma(MmArgs args) {
             if (!found) {
               found = true;
               const int nd = ga_anode(grp, m);
-              const int32_t *gp = &s.gd[cx & 3][rr][0];
+              const int32_t *gp = &s.gd[cx & 7][rr][0];
               g[0] = gp[nd]; g[1] = gp[9 + nd]; g[2] = gp[21 + nd];
             }
           }
         } else if (col_ok(c) && row_owned(rowq + 1)) {
           active = true;
-          const int32_t *gp = &s.gd[c & 3][rowq + 1][18];
+          const int32_t *gp = &s.gd[c & 7][rowq + 1][18];
           g[0] = gp[0]; g[1] = gp[1]; g[2] = gp[2];
         }
       }
@@ -283,11 +349,23 @@ __global__ void __launch_bounds__(MM_NT, 2) k_mma(MmArgs args) {
         }
       }
     };
-    auto lists_parity = [&](int c) {  // after this thread's cp.async copies have landed
-      if (at >= QH * 5) return;
-      const int rowq = at / 5, grp = at - rowq * 5;
+    // ... and the "same P entries as the previous column" test: the constant P-block entries keep their staging positions
+    // from column to column as long as rank classes, base parities of the U and P lists and the column validity do not
+    // change (the staging buffer is never cleared and nobody else writes those positions), so p_entries runs only when
+    // this thread-wide vote finds a difference (the interior of a mesh: once per x-chunk).
+    auto lists_parity = [&](int c) {  // after this thread's cp.async copies have landed (end of step c-1)
+      if (at == 0) s.pdiff[(c + 2) & 3] = 0;  // (read at step c+2, voted at the end of step c+1)
+      if (lt < 0 || lt >= QH * 5) return;
+      const int rowq = lt / 5, grp = lt - rowq * 5;
       const long long *lb = &s.lbase[c & 3][rowq][grp * 3];
-      s.par[c & 3][rowq][grp] = (uint8_t)((lb[0] & 1) | ((lb[1] & 1) << 1) | ((lb[2] & 1) << 2));
+      const uint8_t pb = (uint8_t)((lb[0] & 1) | ((lb[1] & 1) << 1) | ((lb[2] & 1) << 2));
+      s.par[c & 3][rowq][grp] = pb;
+      bool diff = ((pb ^ s.par[(c - 1) & 3][rowq][grp]) & (grp < 4 ? 3 : 7)) != 0;
+      if (grp == 0) {  // classes of the cells of this quad row (and of the halo row by the thread of row 0) in columns c, c-1, c-2
+        for (int rr = rowq == 0 ? 0 : rowq + 1; rr <= rowq + 1; ++rr)
+          if (row_in_table(rr)) diff = diff || s.cls[c & 7][rr] != s.cls[(c - 1) & 7][rr] || s.cls[(c - 1) & 7][rr] != s.cls[(c - 2) & 7][rr];
+      }
+      if (diff) s.pdiff[c & 3] = 1;
     };
     // write-out descriptor of list `at` of quad column c (one step after its base / end have landed, off the critical path)
     auto list_desc = [&](int c) {
@@ -338,7 +416,7 @@ __global__ void __launch_bounds__(MM_NT, 2) k_mma(MmArgs args) {
         const int rr = rowq + 1 - pe_dy;
         own[rowq] = row_owned(rr);
         const bool ok = rowq < nqr && row_in_table(rr) && (own[rowq] || !pe_plist);
-        const int cl = ok ? s.cls[cx & 3][rr] : pe_cls0;
+        const int cl = ok ? s.cls[cx & 7][rr] : pe_cls0;
         rk[rowq] = !ok ? 0xFF : (cl == pe_cls0 ? pe_rk0 : (int)GA_LDG(a.ctab + (int64_t)cl * 900 + pe_rk));
       }
 #pragma unroll
@@ -348,60 +426,37 @@ __global__ void __launch_bounds__(MM_NT, 2) k_mma(MmArgs args) {
         stg0[rowq * GA_QSTRIDE + par + rk[rowq]] = own[rowq] ? pe_val : 0.0;
       }
     };
-    // (A7) write-out of quad column X: plain 16-byte vector stores, one aux warp per quad row and list.  (A TMA bulk copy per
-    //      list -- k_gath's way -- has a read-completion latency of several thousand cycles, profiles/r02_ubench_bulk_copy_rate.txt:
-    //      with ONE staging buffer the main warps would wait for it every column; a store has released its staging bytes as
-    //      soon as it has issued.)  Lists are staged at slot + (base & 1), so source and destination are 16-byte aligned together.
-    //      Descriptors (staging offset, chunks, offset in nzval) are left by list_desc; a warp walks 30 lists four at a
-    //      time: an 8-lane group copies one list (at most 45 chunks: 6 rounds), 128 contiguous bytes per group and instruction.
-    const int awarp = warp - MM_NMW;
-    auto write_out = [&](int X) {
-      const double2 *st2 = reinterpret_cast<const double2 *>(s.stage);
-      const int sub = lane & 7;
-      const uint4 *wd = &s.wd[X & 1][awarp * 32 + (lane >> 3)];
-#pragma unroll 2
-      for (int it = 0; it < 8; ++it) {
-        if (awarp * 32 + 4 * it >= QH * 15) break;  // (120 lists: the last warp has 24)
-        const uint4 e = wd[4 * it];
-        const int nch = (int)(e.y & 255);
-        double *gp = a.nz + (((unsigned long long)e.w << 32) | e.z);
-        double2 *d2 = reinterpret_cast<double2 *>(gp);
-        const double2 *s2 = st2 + e.x;
-        double2 v[6];
-#pragma unroll
-        for (int r = 0; r < 6; ++r)
-          if (sub + 8 * r < nch) v[r] = s2[sub + 8 * r];
-        const bool head = sub == 0 && ((e.y >> 8) & 1), tail = sub == 1 && ((e.y >> 9) & 1);
-        double vh = 0.0;
-        if (head) vh = reinterpret_cast<const double *>(s2)[-1];
-        if (tail) vh = reinterpret_cast<const double *>(s2)[2 * nch];
-#pragma unroll
-        for (int r = 0; r < 6; ++r)
-          if (sub + 8 * r < nch) d2[sub + 8 * r] = v[r];
-        if (head) gp[-1] = vh;
-        if (tail) gp[2 * nch] = vh;
-      }
-    };
-
+    // Step X: the gathers issued here (dof ids of column X+5, iterate values / viscosity / rank class of X+3, list bases of
+    // X+2) form one cp.async group that only has to land by the END of the NEXT step (wait_group 1): no memory latency on
+    // the step's critical path.  Consumers: issue_val(c) reads the dof ids of c two steps after their issue, state(c) the
+    // values of c two steps after theirs, lists_parity(c) the bases of c one step after theirs.
     unsigned phase = 0;
-    for (int X = X0 - 4; X < X1; ++X) {
+    for (int X = X0 - MM_WARM; X < X1; ++X) {
       const bool live = X >= X0;
+      MM_T(7);
       if (live && X > X0 && jac) write_out(X - 1);
       mm_mbar_arrive(&s.mbar_free);        // my stores of column X-1 have issued: their staging bytes are released
+      MM_T(0);
       if (live && jac) list_desc(X);
-      issue_gd(X + 3);
-      issue_val(X + 2);
-      if (X + 1 >= X0 && X + 1 < X1) issue_lists(X + 1);
-      if (live && jac) {
+      issue_gd(X + 5);
+      issue_val(X + 3);
+      if (X + 2 >= X0 && X + 2 < X1) issue_lists(X + 2);
+      ga_cp_commit();
+      MM_T(1);
+      if (live && jac && (X < X0 + 3 || X + 1 >= a.nx || s.pdiff[X & 3] != 0)) {  // (uniform over the aux warps)
         mm_mbar_wait(&s.mbar_free, phase);  // ... and everybody else's
         p_entries(X);
       }
       phase ^= 1;
-      ga_cp_wait_all();
+      MM_T(2);
+      ga_cp_wait_prev();                   // the group of step X-1 has landed
+      MM_T(3);
       if (X + 1 >= X0 && X + 1 < X1) lists_parity(X + 1);
-      ga_bar_step<NT>();  // lists of column X staged, state of X+1 ready, asynchronous copies landed
+      MM_T(4);
+      ga_bar_step<NT>();  // lists of column X staged, state of X+1 ready
     }
     if (jac) write_out(X1 - 1);  // last column of the chunk
+    ga_cp_wait_all();            // (gathers issued for columns beyond the chunk)
   } else {
 #ifndef GM_EMU
     mm_reg_inc<MM_REG_MAIN>();
@@ -415,6 +470,7 @@ __global__ void __launch_bounds__(MM_NT, 2) k_mma(MmArgs args) {
     uint32_t bmask[2];    // per tile slot: variant mask of B column g
     int tile8[2];         // per tile slot: 8 * tile id
     uint32_t tvar[2];     // per tile slot: variants of the tile (union over its columns)
+    uint32_t ebase[2][2]; // per tile slot and accumulator column: first staging slot | slot stride << 10 | owner type << 20
     uint32_t selfast[2];  // per tile slot: epilogue selection of the two accumulator columns when both cell columns exist
     // epilogue selection of output `ow` (packed MmOut) for accumulator row g: which cell supplies the rank record
     // (any cell in the table that contains both nodes), how many owned cells are summed.
@@ -444,7 +500,7 @@ __global__ void __launch_bounds__(MM_NT, 2) k_mma(MmArgs args) {
 #pragma unroll
       for (int w = 0; w < 4; ++w)
         if (warp == w) t = mm_warp_tile(w, sl);
-      bmask[sl] = 0; selfast[sl] = 0; tile8[sl] = 8 * t; tvar[sl] = 0;
+      bmask[sl] = 0; selfast[sl] = 0; tile8[sl] = 8 * t; tvar[sl] = 0; ebase[sl][0] = ebase[sl][1] = 0;
 #pragma unroll
       for (int k = 0; k < 8; ++k) Bt[sl][k] = 0.0;
       if (t < 0) continue;
@@ -461,11 +517,46 @@ __global__ void __launch_bounds__(MM_NT, 2) k_mma(MmArgs args) {
 #pragma unroll
       for (int tt = 0; tt < 8; ++tt)
         if (t == tt) tvar[sl] = (uint32_t)mm_tvar(tt);
+      if ((tvar[sl] & (tvar[sl] - 1)) == 0) {  // single-variant tile (every column takes part): fold the variant's signs into B once
+        const uint32_t tvv = tvar[sl];
+        const int m = tvv == 1 ? 0 : (tvv == 2 ? 1 : (tvv == 4 ? 2 : 3));
+        const double sxy = (m == 1 || m == 2) ? -1.0 : 1.0, sx = (m & 1) ? -1.0 : 1.0, sy = (m & 2) ? -1.0 : 1.0;
+        Bt[sl][MB_PXY] *= sxy; Bt[sl][MB_PYX] *= sxy; Bt[sl][MB_PS] *= sxy; Bt[sl][MB_EX] *= sx; Bt[sl][MB_EY] *= sy;
+      }
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {  // staging offsets of the three lists of the owner of accumulator column 2 j + c
+        const int Ao = s.out[t * 8 + 2 * j + c] & 255;
+        const int slot0 = Ao == 0 ? 0 : (Ao == 1 ? 258 : (Ao == 2 ? 414 : 570)), slen = Ao == 0 ? 90 : (Ao == 3 ? 34 : 54);
+        ebase[sl][c] = (uint32_t)slot0 | ((uint32_t)slen << 10) | ((uint32_t)Ao << 20);
+      }
       selfast[sl] = select(s.out[t * 8 + 2 * j], true, true) | (select(s.out[t * 8 + 2 * j + 1], true, true) << 16);
     }
-    int xm3 = (((X0 - 4) % 3) + 3) % 3;
+    int xm3 = (((X0 - MM_WARM) % 3) + 3) % 3;
     unsigned phase = 0;
     bool stage_ok = false;  // this step's "stage free" wait is done
+
+    // ---- rank records of the two accumulator columns of both tiles: needed in the epilogues only, fetched first thing in a
+    //      step so that their latency (a class lookup, then the record: shared memory for the strip's reference class, L2 else)
+    //      is hidden behind the passes.
+    uint32_t selx[2][2];
+    uint4 recx[2][2];
+    auto fetch_records = [&](int X) {
+      const bool okL = X > 0, okR = X < a.nx;
+#pragma unroll
+      for (int sl = 0; sl < 2; ++sl) {
+        const uint32_t sf = (okL && okR) ? selfast[sl] : (select(s.out[tile8[sl] + 2 * j], okL, okR) | (select(s.out[tile8[sl] + 2 * j + 1], okL, okR) << 16));
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const uint32_t se = (sf >> (16 * c)) & 0xFFFFu;
+          selx[sl][c] = se;
+          const int cx = X - (int)((se >> 11) & 1);
+          const int cl = (se >> 15) ? s.cls[cx & 7][(se >> 7) & 15] : cls0;
+          uint4 r = s.prec[se & 127];
+          if (cl != cls0) r = GA_LDG(reinterpret_cast<const uint4 *>(a.ptab) + ((int64_t)cl * 81 + (se & 127)));
+          recx[sl][c] = r;
+        }
+      }
+    };
 
     // ---- one accumulator tile of quad column X (the tile in slot SL of this warp).  The variant loop is a run-time loop
     //      and all four main warps run the same code (tile id, variant set and column mask are per-warp registers): the
@@ -475,22 +566,8 @@ __global__ void __launch_bounds__(MM_NT, 2) k_mma(MmArgs args) {
       const int T8 = tile8[SL];  // 8 * tile id
       const uint32_t tv = tvar[SL];
       const bool okL = X > 0, okR = X < a.nx;
-      // rank records of my two accumulator columns (issued first: they are needed in the epilogue only)
-      uint32_t sel[2];
-      uint4 rec[2];
-      {
-        const uint32_t sf = (okL && okR) ? selfast[SL] : (select(s.out[T8 + 2 * j], okL, okR) | (select(s.out[T8 + 2 * j + 1], okL, okR) << 16));
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          sel[c] = (sf >> (16 * c)) & 0xFFFFu;
-          rec[c] = uint4{0, 0, 0, 0};
-          if (sel[c] >> 15) {
-            const int cx = X - (int)((sel[c] >> 11) & 1);
-            const int cl = s.cls[cx & 3][(sel[c] >> 7) & 15];
-            rec[c] = cl == cls0 ? s.prec[sel[c] & 127] : GA_LDG(reinterpret_cast<const uint4 *>(a.ptab) + ((int64_t)cl * 81 + (sel[c] & 127)));
-          }
-        }
-      }
+      const uint32_t *sel = selx[SL];  // epilogue selection and rank records: fetched at the start of the step (fetch_records)
+      const uint4 *rec = recx[SL];
       double v00[2] = {0, 0}, v11[2] = {0, 0}, v01[2] = {0, 0}, v10[2] = {0, 0}, ee[2] = {0, 0}, tu0[2] = {0, 0}, tu1[2] = {0, 0};
 #pragma unroll 1
       for (int m = 0; m < 4; ++m) {
@@ -498,11 +575,16 @@ __global__ void __launch_bounds__(MM_NT, 2) k_mma(MmArgs args) {
         const int mx = m & 1, my = m >> 1;
         if (!(mx ? okL : okR)) continue;
         const double *P = s.st[mx ? (xm3 == 0 ? 2 : xm3 - 1) : xm3] + (g + 1 - my) * 4 + (j ^ m);
-        const uint32_t mw = ((bmask[SL] >> m) & 1) ? 0xFFFFFFFFu : 0u;  // my B column takes part in this variant
-        const uint32_t sxy = (uint32_t)((m ^ (m >> 1)) & 1) << 31, sx = (uint32_t)mx << 31, sy = (uint32_t)my << 31;
-        const double bPXX = mm_mask(Bt[SL][MB_PXX], mw, 0), bPYY = mm_mask(Bt[SL][MB_PYY], mw, 0), bTM = mm_mask(Bt[SL][MB_TM], mw, 0);
-        const double bPXY = mm_mask(Bt[SL][MB_PXY], mw, sxy), bPYX = mm_mask(Bt[SL][MB_PYX], mw, sxy), bPS = mm_mask(Bt[SL][MB_PS], mw, sxy);
-        const double bEX = mm_mask(Bt[SL][MB_EX], mw, sx), bEY = mm_mask(Bt[SL][MB_EY], mw, sy);
+        // slot 1 always holds a single-variant tile (signs already folded into B, every column takes part); slot 0 masks
+        // the B column of a lane that does not take part in this variant and applies the variant's signs
+        const uint32_t mw = (SL == 1 || ((bmask[SL] >> m) & 1)) ? 0xFFFFFFFFu : 0u;
+        const bool fl = SL == 0 && (tv & (tv - 1)) != 0;
+        const uint32_t sxy = fl ? (uint32_t)((m ^ (m >> 1)) & 1) << 31 : 0u, sx = fl ? (uint32_t)mx << 31 : 0u, sy = fl ? (uint32_t)my << 31 : 0u;
+        const double bPXX = SL ? Bt[SL][MB_PXX] : mm_mask(Bt[SL][MB_PXX], mw, 0), bPYY = SL ? Bt[SL][MB_PYY] : mm_mask(Bt[SL][MB_PYY], mw, 0),
+                     bTM = SL ? Bt[SL][MB_TM] : mm_mask(Bt[SL][MB_TM], mw, 0);
+        const double bPXY = SL ? Bt[SL][MB_PXY] : mm_mask(Bt[SL][MB_PXY], mw, sxy), bPYX = SL ? Bt[SL][MB_PYX] : mm_mask(Bt[SL][MB_PYX], mw, sxy),
+                     bPS = SL ? Bt[SL][MB_PS] : mm_mask(Bt[SL][MB_PS], mw, sxy);
+        const double bEX = SL ? Bt[SL][MB_EX] : mm_mask(Bt[SL][MB_EX], mw, sx), bEY = SL ? Bt[SL][MB_EY] : mm_mask(Bt[SL][MB_EY], mw, sy);
         // all coefficient planes of the pass first (the loads are independent of everything before them)
         double pa[14];
 #pragma unroll
@@ -527,20 +609,22 @@ __global__ void __launch_bounds__(MM_NT, 2) k_mma(MmArgs args) {
       }
       // ---- epilogue: nine entries per output -> staged lists (positions from the rank record; entries without a
       //      position go to the trash element of their slot)
+      MM_T(2);
       if (!stage_ok) { mm_mbar_wait(&s.mbar_free, phase); stage_ok = true; }
+      MM_T(3);
       double *q0 = s.stage + g * GA_QSTRIDE;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         if (!(sel[c] >> 15)) continue;
-        const uint32_t ow = s.out[T8 + 2 * j + c];
-        const int A = ow & 255;
-        const uint32_t pm = s.par[X & 3][g][A];
-        const int slot0 = A == 0 ? 0 : (A == 1 ? 258 : (A == 2 ? 414 : 570)), slen = A == 0 ? 90 : (A == 3 ? 34 : 54);
+        const uint32_t eb = ebase[SL][c];
+        const uint32_t pm = s.par[X & 3][g][eb >> 20];
+        const int slot0 = eb & 1023, slen = (eb >> 10) & 1023;
         double *b0 = q0 + slot0 + (pm & 1), *b1 = q0 + slot0 + slen + ((pm >> 1) & 1), *b2 = q0 + slot0 + 2 * slen + ((pm >> 2) & 1);
         const double cn = (double)((sel[c] >> 12) & 7);
-        const double mb = cn * s.ek[T8 + 2 * j + c][1];
+        const double2 ekv = *reinterpret_cast<const double2 *>(&s.ek[T8 + 2 * j + c][0]);  // TK, sum_q w phi_i phi_j
+        const double mb = cn * ekv.y;
         const double ut0 = -a.RaPr * a.gx * mb, ut1 = -a.RaPr * a.gy * mb;
-        const double e = ee[c], tt = fma(cn, s.ek[T8 + 2 * j + c][0], e);
+        const double e = ee[c], tt = fma(cn, ekv.x, e);
         const double w00 = v00[c] + e, w11 = v11[c] + e;
         double e00, e01, e02, e10, e11, e12, e20, e21, e22;  // [list k][minor dof l]
         if (CSR) { e00 = w00; e01 = v01[c]; e02 = ut0; e10 = v10[c]; e11 = w11; e12 = ut1; e20 = tu0[c]; e21 = tu1[c]; e22 = tt; }
@@ -647,19 +731,28 @@ __global__ void __launch_bounds__(MM_NT, 2) k_mma(MmArgs args) {
     };
 
     using std::integral_constant;
-    for (int X = X0 - 4; X < X1; ++X) {
+    for (int X = X0 - MM_WARM; X < X1; ++X) {
       const bool live = X >= X0;
       stage_ok = false;
+      MM_T(7);
+      if (live && jac) fetch_records(X);
       // (the tasks that do not touch the staging buffer come first: the write-out of column X-1 is still reading it)
       if (warp == MM_WARP_RESIDUAL && live && res) residual_task(X);
       if (warp == MM_WARP_STATE) state_task(X + 1, xm3 == 2 ? 0 : xm3 + 1);
+      MM_T(1);
       if (live && jac) {
         tile(integral_constant<int, 0>{}, X);
+        MM_T(5);
         tile(integral_constant<int, 1>{}, X);
+        MM_T(6);
       }
       phase ^= 1;
       xm3 = xm3 == 2 ? 0 : xm3 + 1;
       ga_bar_step<NT>();
     }
   }
+#if defined(MM_PROF) && !defined(GM_EMU)
+  if (prof_on)
+    for (int k = 0; k < 8; ++k) mm_prof[warp][k] = pacc[k];
+#endif
 }

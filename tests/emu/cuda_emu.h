@@ -104,6 +104,18 @@ static inline void ga_cp_wait_all() {
   for (auto &c : t_emu_cp) memcpy(c.dst, c.src, c.bytes);
   t_emu_cp.clear();
 }
+// groups (k_mma): copies are performed as LATE as the program allows -- when the thread waits for their group
+static thread_local std::vector<size_t> t_emu_cp_groups;  // end index (in t_emu_cp) of every committed group
+static inline void ga_cp_commit() { t_emu_cp_groups.push_back(t_emu_cp.size()); }
+static inline void ga_cp_wait_prev() {  // wait_group 1: everything but the newest committed group
+  if (t_emu_cp_groups.size() < 2) return;
+  const size_t n = t_emu_cp_groups[t_emu_cp_groups.size() - 2];
+  for (size_t k = 0; k < n; ++k) memcpy(t_emu_cp[k].dst, t_emu_cp[k].src, t_emu_cp[k].bytes);
+  t_emu_cp.erase(t_emu_cp.begin(), t_emu_cp.begin() + n);
+  const size_t last = t_emu_cp_groups.back() - n;
+  t_emu_cp_groups.clear();
+  t_emu_cp_groups.push_back(last);
+}
 static int64_t g_emu_bulk_misaligned = 0;
 static inline void ga_bulk_store(double *g, const double *s, int bytes) {
   if (((uintptr_t)g & 15) || ((uintptr_t)s & 15) || (bytes & 15) || bytes <= 0) __atomic_add_fetch(&g_emu_bulk_misaligned, 1, __ATOMIC_RELAXED);
@@ -129,7 +141,7 @@ static void *emu_thread_main(void *p) {
   EmuLaunch<Args> *l = (EmuLaunch<Args> *)p;
   threadIdx.x = l->t; threadIdx.y = 0; threadIdx.z = 0;
   blockIdx = l->bidx;
-  t_emu_cp.clear(); t_emu_bulk.clear();
+  t_emu_cp.clear(); t_emu_bulk.clear(); t_emu_cp_groups.clear();
   l->kernel(l->args);
   return nullptr;
 }
