@@ -35,6 +35,8 @@
 #define MM_NR (MM_QH + 1)            // cell rows of state (one halo row below)
 #define MM_PST (MM_NR * 4)           // doubles per state plane: [cell row][point]
 #define MM_VST 36                    // row stride of the staged iterate values (30 used; k-steps read up to index 32; bank spread)
+#define MM_QSTRIDE 738               // staged doubles per quad row: 15 list slots (728) + pad; = 2 mod 16, so that the eight rows an
+                                     // epilogue store touches start in eight different 8-byte bank pairs (732 mapped rows r and r+4 together)
 #define MM_NMW 4                     // main warps
 #define MM_NAW 4                     // aux warps
 #define MM_NT ((MM_NMW + MM_NAW) * 32)
@@ -88,7 +90,7 @@ __device__ long long mm_prof[8][8];
 #endif
 
 struct MmSmem {
-  double stage[MM_QH * GA_QSTRIDE];    // staged lists of the quad column being assembled
+  double stage[MM_QH * MM_QSTRIDE];    // staged lists of the quad column being assembled
   double st[3][MM_NPL * MM_PST];       // state ring (cell column mod 3), plane-major
   double val[4][MM_NR][MM_VST];        // iterate values of cell column c (c & 3)
   double visc[4][MM_NR][4][2];
@@ -377,7 +379,7 @@ __global__ void __launch_bounds__(MM_NT, 2) k_mma(MmArgs args) {
         const int len = (int)(s.lnext[c & 3][rowq][li] - base), par = (int)(base & 1);
         const unsigned long long off = (unsigned long long)(base + par);  // first 16-byte chunk in nzval (doubles)
         // x: first chunk in the staging buffer (16-byte units); y: chunks | odd head << 8 | odd tail << 9; (z, w): off
-        d = uint4{(uint32_t)((rowq * GA_QSTRIDE + s.slot[li]) / 2 + par), (uint32_t)((len - par) >> 1) | ((uint32_t)par << 8) | ((uint32_t)((len - par) & 1) << 9),
+        d = uint4{(uint32_t)((rowq * MM_QSTRIDE + s.slot[li]) / 2 + par), (uint32_t)((len - par) >> 1) | ((uint32_t)par << 8) | ((uint32_t)((len - par) & 1) << 9),
                   (uint32_t)off, (uint32_t)(off >> 32)};
       }
       s.wd[c & 1][at] = d;
@@ -423,7 +425,7 @@ __global__ void __launch_bounds__(MM_NT, 2) k_mma(MmArgs args) {
       for (int rowq = 0; rowq < QH; ++rowq) {
         if (rk[rowq] == 0xFF) continue;
         const int par = (s.par[X & 3][rowq][pe_li / 3] >> (pe_li % 3)) & 1;
-        stg0[rowq * GA_QSTRIDE + par + rk[rowq]] = own[rowq] ? pe_val : 0.0;
+        stg0[rowq * MM_QSTRIDE + par + rk[rowq]] = own[rowq] ? pe_val : 0.0;
       }
     };
     // Step X: the gathers issued here (dof ids of column X+5, iterate values / viscosity / rank class of X+3, list bases of
@@ -612,7 +614,7 @@ __global__ void __launch_bounds__(MM_NT, 2) k_mma(MmArgs args) {
       MM_T(2);
       if (!stage_ok) { mm_mbar_wait(&s.mbar_free, phase); stage_ok = true; }
       MM_T(3);
-      double *q0 = s.stage + g * GA_QSTRIDE;
+      double *q0 = s.stage + g * MM_QSTRIDE;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         if (!(sel[c] >> 15)) continue;
