@@ -468,6 +468,9 @@ __global__ void __launch_bounds__(MM_NT, 2) k_mma(MmArgs args) {
     // k = point j.  As accumulator columns: outputs 2 j, 2 j + 1.
     // =====================================================================================
     const int g = lane >> 2, j = lane & 3;
+    // role of this warp (which tiles / tasks): rotated from CTA to CTA, so that the two CTAs of an SM do not put their heaviest
+    // warps (110 tensor instructions per column) on the same sub-partition's tensor pipe
+    const int wrole = (warp + (int)blockIdx.x + (int)blockIdx.y) & 3;
     double Bt[2][8];      // per tile slot: reference-element products of B column g at point j
     uint32_t bmask[2];    // per tile slot: variant mask of B column g
     int tile8[2];         // per tile slot: 8 * tile id
@@ -501,7 +504,7 @@ __global__ void __launch_bounds__(MM_NT, 2) k_mma(MmArgs args) {
       int t = -1;
 #pragma unroll
       for (int w = 0; w < 4; ++w)
-        if (warp == w) t = mm_warp_tile(w, sl);
+        if (wrole == w) t = mm_warp_tile(w, sl);
       bmask[sl] = 0; selfast[sl] = 0; tile8[sl] = 8 * t; tvar[sl] = 0; ebase[sl][0] = ebase[sl][1] = 0;
 #pragma unroll
       for (int k = 0; k < 8; ++k) Bt[sl][k] = 0.0;
@@ -739,8 +742,8 @@ __global__ void __launch_bounds__(MM_NT, 2) k_mma(MmArgs args) {
       MM_T(7);
       if (live && jac) fetch_records(X);
       // (the tasks that do not touch the staging buffer come first: the write-out of column X-1 is still reading it)
-      if (warp == MM_WARP_RESIDUAL && live && res) residual_task(X);
-      if (warp == MM_WARP_STATE) state_task(X + 1, xm3 == 2 ? 0 : xm3 + 1);
+      if (wrole == MM_WARP_RESIDUAL && live && res) residual_task(X);
+      if (wrole == MM_WARP_STATE) state_task(X + 1, xm3 == 2 ? 0 : xm3 + 1);
       MM_T(1);
       if (live && jac) {
         tile(integral_constant<int, 0>{}, X);
