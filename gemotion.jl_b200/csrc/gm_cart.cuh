@@ -358,22 +358,23 @@ static int gm_gath_launch(gm_handle *h, const CartArgs &a, bool csr, bool newt) 
   return newt ? gm_gath_launch1<NG, false, true>(h, a) : gm_gath_launch1<NG, false, false>(h, a);
 }
 
-// ---- k_mma (gm_mma_kernel.cuh): 4 main + 4 aux warps, 8 quad rows, two CTAs per SM
-template <bool CSR, bool NEWT, int XCH>
-static int gm_mma_launch2(gm_handle *h, const CartArgs &a, int nstrips) {
+// ---- k_mma (gm_mma_kernel.cuh): 4 main + 4 aux warps, 8 quad rows, two CTAs per SM.  Strips [strip0, strip0 + nstrips) on `stream`.
+template <bool CSR, bool NEWT>
+static int gm_mma_launch2(gm_handle *h, const CartArgs &a, int xch, int strip0, int nstrips, cudaStream_t stream) {
   const size_t sm = sizeof(MmSmem);
-  GM_CUDA(cudaFuncSetAttribute(k_mma<CSR, NEWT, XCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));  // (per device: set on every launch)
-  GM_CUDA(cudaFuncSetAttribute(k_mma<CSR, NEWT, XCH>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));  // two CTAs per SM
+  GM_CUDA(cudaFuncSetAttribute(k_mma<CSR, NEWT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));  // (per device: set on every launch)
+  GM_CUDA(cudaFuncSetAttribute(k_mma<CSR, NEWT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));  // two CTAs per SM
   MmArgs ma;
   ma.a = a;
   memcpy(ma.out, MM_OUT, sizeof ma.out);
-  dim3 grid((a.nx + 1 + XCH - 1) / XCH, nstrips);
-  k_mma<CSR, NEWT, XCH><<<grid, MM_NT, sm, h->stream>>>(ma);
+  ma.xch = xch;
+  ma.strip0 = strip0;
+  dim3 grid((a.nx + 1 + xch - 1) / xch, nstrips);
+  k_mma<CSR, NEWT><<<grid, MM_NT, sm, stream>>>(ma);
 #ifdef MM_PROF
-  {  // development build: cycles per warp and phase of the middle CTA (main: 0 write-out, 1 residual / state, 2 passes, 3 stage wait,
-     // 5 / 6 epilogues of slot 0 / 1, 7 barrier; aux: 0 write-out, 1 gathers, 2 P entries, 3 cp.async wait, 4 parities, 7 barrier)
+  {  // development build: cycles per warp and phase of the middle CTA (profiles/r02_k_mma_phase_timing.txt)
     long long hp[8][8];
-    cudaStreamSynchronize(h->stream);
+    cudaStreamSynchronize(stream);
     cudaMemcpyFromSymbol(hp, mm_prof, sizeof hp);
     for (int w = 0; w < 8; ++w) {
       fprintf(stderr, "mm_prof warp %d:", w);
@@ -384,16 +385,9 @@ static int gm_mma_launch2(gm_handle *h, const CartArgs &a, int nstrips) {
 #endif
   return GM_OK;
 }
-template <bool CSR, bool NEWT>
-static int gm_mma_launch1(gm_handle *h, const CartArgs &a, int xch) {
-  const int nstrips = (a.row_end - a.row_begin + 1 + MM_QH - 1) / MM_QH;
-  if (xch == 0) xch = gm_gath_chunk(a.nx, nstrips, 2 * h->num_sms);
-  return xch <= 32 ? gm_mma_launch2<CSR, NEWT, 32>(h, a, nstrips)
-         : xch <= 128 ? gm_mma_launch2<CSR, NEWT, 128>(h, a, nstrips) : gm_mma_launch2<CSR, NEWT, 256>(h, a, nstrips);
-}
-static int gm_mma_launch(gm_handle *h, const CartArgs &a, bool csr, bool newt, int xch) {
-  if (csr) return newt ? gm_mma_launch1<true, true>(h, a, xch) : gm_mma_launch1<true, false>(h, a, xch);
-  return newt ? gm_mma_launch1<false, true>(h, a, xch) : gm_mma_launch1<false, false>(h, a, xch);
+static int gm_mma_launch(gm_handle *h, const CartArgs &a, bool csr, bool newt, int xch, int strip0, int nstrips, cudaStream_t stream) {
+  if (csr) return newt ? gm_mma_launch2<true, true>(h, a, xch, strip0, nstrips, stream) : gm_mma_launch2<true, false>(h, a, xch, strip0, nstrips, stream);
+  return newt ? gm_mma_launch2<false, true>(h, a, xch, strip0, nstrips, stream) : gm_mma_launch2<false, false>(h, a, xch, strip0, nstrips, stream);
 }
 
 static int gm_cart_run(gm_handle *h, const double *d_x, double *d_nz, double *d_b, unsigned flags, int64_t *launches) {
@@ -413,8 +407,31 @@ static int gm_cart_run(gm_handle *h, const double *d_x, double *d_nz, double *d_
     ++*launches;
   }
   const bool csr = h->d.layout == GM_LAYOUT_CSR;
-  if (c->kernel == GM_KERNEL_MMA) rc = gm_mma_launch(h, a, csr, newt, h->d.xchunk);
-  else if (c->use_sweep) rc = gm_cart_launch<4>(h, a, csr, newt);
+  if (c->kernel == GM_KERNEL_MMA) {
+    const int nstrips = (a.row_end - a.row_begin + 1 + MM_QH - 1) / MM_QH;
+    const int xch = h->d.xchunk > 0 ? h->d.xchunk : gm_mma_chunk(a.nx, nstrips, 2 * h->num_sms, MM_WARM);
+    gm_multi *m = (gm_multi *)h->multi;
+    const bool overlap = m && m->comm && !(flags & GM_NO_EXCHANGE) && (h->d.ghost_lo || h->d.ghost_hi);
+    if (overlap) {
+      // the strip next to the lower interface first, on the high-priority exchange stream; its lists are packed and
+      // sent to rank-1 (and the lists of rank+1 received) while the remaining strips run on the main stream
+      GM_CUDA(cudaEventRecord(m->ev_fork, h->stream));
+      GM_CUDA(cudaStreamWaitEvent(m->xstream, m->ev_fork, 0));
+      const int first = (h->d.ghost_lo && nstrips > 1) ? 1 : 0;  // strips [0, first) go to the exchange stream
+      if (first) { rc = gm_mma_launch(h, a, csr, newt, xch, 0, first, m->xstream); ++*launches; }
+      if (rc) return rc;
+      rc = gm_mma_launch(h, a, csr, newt, xch, first, nstrips - first, h->stream);
+      ++*launches;
+      if (rc) return rc;
+      GM_CUDA(cudaGetLastError());
+      if (h->d.ghost_lo && !first) {  // a single strip: the pack must wait for it
+        GM_CUDA(cudaEventRecord(m->ev_join, h->stream));
+        GM_CUDA(cudaStreamWaitEvent(m->xstream, m->ev_join, 0));
+      }
+      return gm_multi_exchange_overlapped(h, d_nz, d_b, flags, launches);
+    }
+    rc = gm_mma_launch(h, a, csr, newt, xch, 0, nstrips, h->stream);
+  } else if (c->use_sweep) rc = gm_cart_launch<4>(h, a, csr, newt);
   else rc = c->gath_ng == 1 ? gm_gath_launch<1>(h, a, csr, newt) : gm_gath_launch<2>(h, a, csr, newt);
   if (rc) return rc;
   ++*launches;

@@ -89,6 +89,24 @@ static inline int gm_gath_chunk(int nx, int nstrips, int nsm) {
   return (long long)((nx + 1 + 255) / 256) * nstrips < 12LL * nsm ? 128 : 256;
 }
 
+// x-chunk length of k_mma (a run-time argument).  A CTA sweeps `warm` warm-up columns + one chunk; `slots` CTAs are
+// resident at a time (2 per SM), so a launch of nstrips x nchunks CTAs takes ceil(nstrips * nchunks / slots) waves of
+// (chunk + warm) column steps.  Picks the chunk in [96, 768] that minimises that estimate (the fixed 256 / 128 choice of
+// k_gath left the last wave 27 % full on 8 GPUs: 65 strips x 17 chunks on 296 slots).
+static inline int gm_mma_chunk(int nx, int nstrips, int slots, int warm) {
+  long long best = -1;
+  int best_ch = 256;
+  for (int pass = 0; pass < 2 && best < 0; ++pass)  // first only chunkings with at least four waves (load balance, and the
+    for (int ch = 96; ch <= 768; ch += 4) {          // interface strip of a multi-GPU rank finishes early), then any
+      const long long nchunks = (nx + 1 + ch - 1) / ch;
+      const long long waves = (nchunks * nstrips + slots - 1) / slots;
+      if (pass == 0 && waves < 4) continue;
+      const long long cost = waves * (ch + warm);
+      if (best < 0 || cost * 200 < best * 199) { best = cost; best_ch = ch; }  // (a longer chunk must win by 0.5 %)
+    }
+  return best_ch;
+}
+
 // Pair-major copy of the class tables for k_gath: record [class][major node M][minor node m] holds the 9
 // ranks (list k of M) x (dof l of m) at byte k*3+l (bytes 9..15 unused), so a lane fetches them with one
 // 16-byte load.  ctab is [nclass][900] = rank[minor dof][major dof].  Entries without a position

@@ -65,6 +65,8 @@ struct gm_handle {
   int64_t d_nz_cap = 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   gm_times times;
+  bool times_pending = false;  // kernel_ms / exchange_ms of the last device assembly not read back yet
+  int64_t n_owned = 0;         // dofs owned by this rank (row blocks); 0: all
   int64_t device_bytes = 0;
 };
 

@@ -404,6 +404,7 @@ extern "C" int gm_assemble_device(gm_handle *h, const double *d_x, double *d_nzv
   if (!h || !d_x) { gm_set_error("gm_assemble_device: null argument"); return GM_ERR_ARG; }
   GM_CUDA(cudaSetDevice(h->dev));
   int64_t launches = 0;
+  if (h->multi) ((gm_multi *)h->multi)->timed = false;
   GM_CUDA(cudaEventRecord(h->ev[1], h->stream));
   int rc = gm_run(h, d_x, d_nzval, d_resid, flags, &launches);
   if (rc) return rc;
@@ -411,18 +412,9 @@ extern "C" int gm_assemble_device(gm_handle *h, const double *d_x, double *d_nzv
   h->times.launches = launches;
   h->times.h2d_ms = h->times.d2h_ms = 0;
   h->times.h2d_bytes = h->times.d2h_bytes = 0;
-  if (sync) {
-    GM_CUDA(cudaStreamSynchronize(h->stream));
-    float ms = 0;
-    GM_CUDA(cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]));
-    h->times.kernel_ms = ms;
-    gm_multi *m = (gm_multi *)h->multi;
-    h->times.exchange_ms = 0;
-    if (m && m->comm && !(flags & GM_NO_EXCHANGE)) {
-      GM_CUDA(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
-      h->times.exchange_ms = ms;
-    }
-  }
+  h->times.kernel_ms = h->times.exchange_ms = -1.0;  // filled by gm_timing once the events have completed
+  h->times_pending = true;
+  if (sync) GM_CUDA(cudaStreamSynchronize(h->stream));
   return GM_OK;
 }
 
@@ -470,13 +462,28 @@ extern "C" int gm_assemble(gm_handle *h, const double *x, double *nzval, double 
 
 extern "C" int gm_timing(gm_handle *h, gm_times *t) {
   if (!h || !t) { gm_set_error("gm_timing: null argument"); return GM_ERR_ARG; }
+  if (h->times_pending) {  // device entry point: the step may have been asynchronous; wait for its last event now
+    GM_CUDA(cudaSetDevice(h->dev));
+    GM_CUDA(cudaEventSynchronize(h->ev[2]));
+    float ms = 0;
+    GM_CUDA(cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]));
+    h->times.kernel_ms = ms;
+    h->times.exchange_ms = 0;
+    gm_multi *m = (gm_multi *)h->multi;
+    if (m && m->timed) {
+      GM_CUDA(cudaEventSynchronize(m->ev1));
+      GM_CUDA(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
+      h->times.exchange_ms = ms;  // pack + NCCL send / receive + unpack-add (overlapped with the interior strips by k_mma)
+    }
+    h->times_pending = false;
+  }
   *t = h->times;
   return GM_OK;
 }
 
 extern "C" int gm_info(gm_handle *h, int64_t *n_owned, int32_t *active_path, int32_t *ncolors, int64_t *device_bytes) {
   if (!h) { gm_set_error("gm_info: null handle"); return GM_ERR_ARG; }
-  if (n_owned) *n_owned = h->n_total;
+  if (n_owned) *n_owned = h->n_owned > 0 ? h->n_owned : h->n_total;
   if (active_path) *active_path = h->active_path;
   if (ncolors) *ncolors = h->ncolors;
   if (device_bytes) *device_bytes = h->device_bytes;
@@ -507,14 +514,11 @@ extern "C" int gm_comm_init(gm_handle *h, const void *id128) {
   if (!h || !id128) { gm_set_error("gm_comm_init: null argument"); return GM_ERR_ARG; }
   if (h->d.nranks <= 1) return GM_OK;
   GM_CUDA(cudaSetDevice(h->dev));
-  if (!h->multi) {
-    gm_multi *m = new (std::nothrow) gm_multi();
-    if (!m) return GM_ERR_OOM;
-    h->multi = m;
-    GM_CUDA(cudaEventCreate(&m->ev0));
-    GM_CUDA(cudaEventCreate(&m->ev1));
+  gm_multi *m = nullptr;
+  {
+    const int rc0 = gm_multi_get(h, &m);
+    if (rc0) return rc0;
   }
-  gm_multi *m = (gm_multi *)h->multi;
   ncclUniqueId id;
   memcpy(&id, id128, 128);
   GM_NCCL(ncclCommInitRank(&m->comm, h->d.nranks, id, h->d.rank));

@@ -51,6 +51,8 @@ enum { MB_PXX, MB_PYY, MB_PXY, MB_PYX, MB_PS, MB_TM, MB_EX, MB_EY };
 struct MmArgs {
   CartArgs a;
   MmOut out[8][8];
+  int xch;     // quad columns per x-chunk (a CTA sweeps one chunk of one strip)
+  int strip0;  // first strip of this launch (the strip next to the lower rank interface runs first, on its own stream)
 };
 
 // ---- tensor instruction, mbarrier, register reallocation (device) ; the emulation versions live in cuda_emu.h
@@ -123,7 +125,7 @@ __host__ __device__ constexpr int mm_warp_tile(int w, int s) {
 #define MM_WARP_RESIDUAL 2
 #define MM_WARP_STATE 3
 
-template <bool CSR, bool NEWT, int XCH>
+template <bool CSR, bool NEWT>
 __global__ void __launch_bounds__(MM_NT, 2) k_mma(MmArgs args) {
   using S = MmSmem;
   constexpr int QH = MM_QH, NR = MM_NR, NAT = MM_NAW * 32, NT = MM_NT;
@@ -137,10 +139,10 @@ __global__ void __launch_bounds__(MM_NT, 2) k_mma(MmArgs args) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool is_aux = warp >= MM_NMW;
   const int at = tid - MM_NMW * 32;  // aux thread index
-  const int Yq0 = a.row_begin + (int)blockIdx.y * QH;     // first quad row of the strip
+  const int Yq0 = a.row_begin + ((int)blockIdx.y + args.strip0) * QH;  // first quad row of the strip
   const int nqr = min(QH, a.row_end + 1 - Yq0);           // quad rows Yq0 .. Yq0+nqr-1 (row_end = the top mesh line)
   const int Yc0 = Yq0 - 1;                                // cell row of state row 0
-  const int X0 = (int)blockIdx.x * XCH, X1 = min(a.nx + 1, X0 + XCH);  // quad columns of this x-chunk
+  const int X0 = (int)blockIdx.x * args.xch, X1 = min(a.nx + 1, X0 + args.xch);  // quad columns of this x-chunk
   const bool jac = (a.flags & GM_JACOBIAN) != 0, res = (a.flags & GM_RESIDUAL) != 0;
   const CartCell &cc = *a.cc;
 

@@ -74,7 +74,7 @@ class Oracle:
         P = _Problem()
         P.cell_type = m.cell_type
         P.cartesian = 1 if m.cartesian else 0
-        P.ncells, P.nverts = m.ncells, m.nverts
+        P.ncells, P.nverts = int(k["du"].shape[0]), m.nverts  # (a row-block rank holds the cell tables of its rows only)
         P.hx, P.hy = (m.h if m.cartesian else (0.0, 0.0))
         P.coords, P.cell_vertices = _p(k["coords"]), _p(k["cv"])
         P.cell_dofs_u, P.cell_dofs_p, P.cell_dofs_t = _p(k["du"]), _p(k["dp"]), _p(k["dt"])

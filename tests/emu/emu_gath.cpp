@@ -36,15 +36,16 @@ static int run(CartArgs a, bool csr, bool newt) {
   return newt ? emu_launch(k_gath<NG, false, true, XCH>, a, gx, gy, nt, GA_NAUX * 32, sm) : emu_launch(k_gath<NG, false, false, XCH>, a, gx, gy, nt, GA_NAUX * 32, sm);
 }
 
-template <int XCH>
-static int run_mma(const CartArgs &a, bool csr, bool newt) {
+static int run_mma(const CartArgs &a, bool csr, bool newt, int xch) {
   MmArgs ma;
   ma.a = a;
   memcpy(ma.out, MM_OUT, sizeof ma.out);
-  const unsigned gx = (a.nx + 1 + XCH - 1) / XCH, gy = (a.row_end - a.row_begin + 1 + MM_QH - 1) / MM_QH;
+  ma.xch = xch;
+  ma.strip0 = 0;
+  const unsigned gx = (a.nx + 1 + xch - 1) / xch, gy = (a.row_end - a.row_begin + 1 + MM_QH - 1) / MM_QH;
   const size_t sm = sizeof(MmSmem);
-  if (csr) return newt ? emu_launch(k_mma<true, true, XCH>, ma, gx, gy, MM_NT, MM_NAW * 32, sm) : emu_launch(k_mma<true, false, XCH>, ma, gx, gy, MM_NT, MM_NAW * 32, sm);
-  return newt ? emu_launch(k_mma<false, true, XCH>, ma, gx, gy, MM_NT, MM_NAW * 32, sm) : emu_launch(k_mma<false, false, XCH>, ma, gx, gy, MM_NT, MM_NAW * 32, sm);
+  if (csr) return newt ? emu_launch(k_mma<true, true>, ma, gx, gy, MM_NT, MM_NAW * 32, sm) : emu_launch(k_mma<true, false>, ma, gx, gy, MM_NT, MM_NAW * 32, sm);
+  return newt ? emu_launch(k_mma<false, true>, ma, gx, gy, MM_NT, MM_NAW * 32, sm) : emu_launch(k_mma<false, false>, ma, gx, gy, MM_NT, MM_NAW * 32, sm);
 }
 
 extern "C" int emu_gath_run(int nx, int ny, int row_begin, int row_end, const int32_t *gdofs, const double *dvals,
@@ -67,7 +68,7 @@ extern "C" int emu_gath_run(int nx, int ny, int row_begin, int row_end, const in
   a.Pr = prm[0]; a.RaPr = prm[1] * prm[0]; a.gx = prm[4]; a.gy = prm[5]; a.reg = prm[3]; a.n = prm[2]; a.js = prm[6];
   g_emu_bulk_misaligned = 0;
   if (ng == 0) {  // k_mma (gm_mma_kernel.cuh)
-    int rc = xch == 256 ? run_mma<256>(a, csr != 0, newt) : (xch == 128 ? run_mma<128>(a, csr != 0, newt) : run_mma<32>(a, csr != 0, newt));
+    int rc = run_mma(a, csr != 0, newt, xch);
     if (diag) diag[0] = g_emu_bulk_misaligned;
     return rc;
   }

@@ -130,3 +130,27 @@ def test_row_oracle_equals_full_assembly(layout):
             assert np.array_equal(np.diff(rp), ptr[rows + 1] - ptr[rows])
             sel = np.concatenate([np.arange(ptr[r], ptr[r + 1]) for r in rows])
             assert np.array_equal(ri, idx[sel]) and np.array_equal(rv, nz[sel]) and np.array_equal(rb, b[rows])
+
+
+def test_row_oracle_on_row_block_ranks():
+    """bench.py --verify on N GPUs: every rank checks a sample of its OWNED dofs against the row oracle built from its
+    local cell tables (owned rows + ghost rows).  Those lists must be the global matrix's: every incident cell of an
+    owned dof is in the rank's table (owner = lowest row block touching the dof)."""
+    import rowcheck
+    model = fe.CartesianModel((0, 1, 0, 1), (24, 24))
+    full = cases.spaces(model, cases.TURAN)
+    prm = dict(Pr=100.0, Ra=1e5, n=1.4)
+    x = fe.splitmix_iterate(full.n_total, 1234)
+    forc = Oracle(full, **prm)
+    fp, fi = forc.pattern("csc")
+    fnz, fb = forc.assemble(x, "csc")
+    seen = np.zeros(full.n_total, dtype=np.int32)
+    for r in range(3):
+        sp = fe.build_rank_spaces(model, cases.TURAN["V"], cases.TURAN["Ttags"], cases.TURAN["Texpr"], r, 3)
+        seen[fe.owned_dofs(sp)] += 1
+        rows = rowcheck.sample_rows(sp, nrandom=100)
+        assert np.all(np.isin(rows, fe.owned_dofs(sp)))
+        p, i, v, b = Oracle(sp, **prm).rows(rows, x, "csc")
+        sel = np.concatenate([np.arange(fp[q], fp[q + 1]) for q in rows])
+        assert np.array_equal(i, fi[sel]) and np.array_equal(v, fnz[sel]) and np.array_equal(b, fb[rows])
+    assert np.all(seen == 1)
