@@ -1,4 +1,4 @@
-"""Newton driver and `simulate` -- the host loop that CALLS the hot path.
+"""Newton / trust-region drivers -- the host loop that CALLS the hot path.
 
 Mirrors the caller side of the reference: `NLSolver(LUSolver(); nlsolver_opts...)`,
 `FESolver`, `solve` (/root/reference/src/Solver.jl:162-195), i.e. NLsolve 4.5.1 `newton_`
@@ -149,6 +149,109 @@ def newton(op, x0, ftol=1e-8, xtol=0.0, iterations=1000, linesearch="backtrackin
         trace.append((it, fnorm, float(np.linalg.norm(x - xold))))
         if show_trace:
             print("%6d   %14e   %14e" % trace[-1])
+    return NLResult(x, it, f_conv, x_conv, fnorm, f_calls, g_calls, trace, t_asm, t_lin)
+
+
+def _wnorm(d, v):
+    return float(np.sqrt(np.sum((d * v) ** 2)))
+
+
+def _dogleg(lu_solve, A, r, d, delta):
+    """NLsolve `dogleg!` (Nocedal & Wright, eq. 4.16) with the column scaling d: Gauss-Newton step if it lies inside the
+    region, else the Cauchy point along -D^-2 J'r, else the point of the dogleg path on the boundary."""
+    p_i = -lu_solve(r)
+    if _wnorm(d, p_i) <= delta:
+        return p_i
+    g = -(A.T @ r) / d ** 2
+    Jg = A @ g
+    p_c = g * (_wnorm(d, g) ** 2 / float(Jg @ Jg))
+    if _wnorm(d, p_c) >= delta:
+        return p_c * (delta / _wnorm(d, p_c))
+    p_i = p_i - p_c
+    b = 2.0 * float(np.sum(d * p_c * d * p_i))
+    a = _wnorm(d, p_i) ** 2
+    tau = (-b + math.sqrt(b * b - 4.0 * a * (_wnorm(d, p_c) ** 2 - delta ** 2))) / (2.0 * a)
+    return p_c + tau * p_i
+
+
+def trust_region(op, x0, ftol=1e-8, xtol=0.0, iterations=1000, factor=1.0, autoscale=True, show_trace=False) -> NLResult:
+    """NLsolve.nlsolve(df, x0; method=:trust_region, factor=1.0, autoscale=true) -- the driver of
+    /root/reference/examples/validation-basak/basak.jl:20-26 (`linesearch` is ignored by this method).  Restated from the
+    algorithm NLsolve documents (Powell dogleg, N&W ch. 4 / 11; trust radius halved for rho < 0.1, doubled to
+    2 |D p| for rho >= 0.9, scaling d_j = max(0.1 d_j, |J[:, j]|)); NLsolve's source is not in the image, so details such as
+    tie handling are unverified against it."""
+    n = op.n
+    x = np.array(x0, dtype=np.float64, copy=True)
+    r = np.zeros(n)
+    f = np.zeros(n)
+    A = op.allocate_jacobian()
+    t_asm = t_lin = 0.0
+    t0 = time.perf_counter()
+    op.residual_and_jacobian_(r, A, x)
+    t_asm += time.perf_counter() - t0
+    f_calls, g_calls = 1, 1
+    if not np.all(np.isfinite(r)):
+        raise FloatingPointError("non-finite residual at the initial guess")
+
+    def colnorms(M):
+        return np.sqrt(np.asarray(M.multiply(M).sum(axis=0)).ravel())
+
+    d = np.ones(n)
+    if autoscale:
+        d = colnorms(A)
+        d[d == 0.0] = 1.0
+    delta = factor * _wnorm(d, x)
+    if delta == 0.0:
+        delta = factor
+    eta = 1e-4
+    it = 0
+    fnorm = float(np.max(np.abs(r))) if n else 0.0
+    f_conv, x_conv = fnorm <= ftol, False
+    trace = [(0, fnorm, float("nan"))]
+    stopped = False
+    lu = None
+    while not stopped and not (f_conv or x_conv) and it < iterations:
+        it += 1
+        if lu is None:
+            t0 = time.perf_counter()
+            lu = spla.splu(A.tocsc() if A.format != "csc" else A)
+            t_lin += time.perf_counter() - t0
+        t0 = time.perf_counter()
+        p = _dogleg(lu.solve, A, r, d, delta)
+        t_lin += time.perf_counter() - t0
+        xold = x.copy()
+        x = x + p
+        t0 = time.perf_counter()
+        op.residual_(f, x)
+        t_asm += time.perf_counter() - t0
+        f_calls += 1
+        r_predict = A @ p + r
+        rho = (float(r @ r) - float(f @ f)) / (float(r @ r) - float(r_predict @ r_predict))
+        if rho > eta:  # successful iteration
+            r[:] = f
+            t0 = time.perf_counter()
+            op.jacobian_(A, x)
+            t_asm += time.perf_counter() - t0
+            g_calls += 1
+            lu = None
+            if autoscale:
+                d = np.maximum(0.1 * d, colnorms(A))
+            x_conv = float(np.max(np.abs(x - xold))) <= xtol
+            f_conv = float(np.max(np.abs(r))) <= ftol
+        else:
+            x = xold
+            x_conv = f_conv = False
+        if rho < 0.1:
+            delta = delta / 2.0
+        elif rho >= 0.9:
+            delta = 2.0 * _wnorm(d, p)
+        elif rho >= 0.5:
+            delta = max(delta, 2.0 * _wnorm(d, p))
+        stopped = bool(np.any(np.isnan(x)) or np.any(np.isnan(f)))
+        fnorm = float(np.max(np.abs(r)))
+        trace.append((it, fnorm, float(np.linalg.norm(p))))
+        if show_trace:
+            print("%6d   %14e   %14e   rho %10.3e  delta %10.3e" % (it, fnorm, trace[-1][2], rho, delta))
     return NLResult(x, it, f_conv, x_conv, fnorm, f_calls, g_calls, trace, t_asm, t_lin)
 
 

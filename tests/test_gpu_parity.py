@@ -196,6 +196,7 @@ def test_bench_sizes_row_oracle(gm, gpu_lib, N, pi, layout):
         dx = torch.from_numpy(x).cuda()
         dnz = torch.full((nnz,), float("nan"), dtype=torch.float64, device="cuda")
         db = torch.full((sp.n_total,), float("nan"), dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()  # (the handle runs on its own stream: the NaN fill must have finished)
         h.assemble_device(dx.data_ptr(), dnz.data_ptr(), db.data_ptr(), gm.capi.GM_JACOBIAN | gm.capi.GM_RESIDUAL, sync=True)
         assert not bool(torch.isnan(dnz).any()) and not bool(torch.isnan(db).any()), "every entry must be written"
         rows = rowcheck.sample_rows(sp, nrandom=3000)
@@ -238,6 +239,7 @@ def test_row_blocks_emulated_on_one_gpu(gm, gpu_lib, nranks, nx, ny, layout):
         nnz = h.pattern()
         dnz = torch.full((nnz,), float("nan"), dtype=torch.float64, device="cuda")
         db = torch.full((full.n_total,), float("nan"), dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()  # (the handle runs on its own stream)
         h.assemble_device(dx.data_ptr(), dnz.data_ptr(), db.data_ptr(), flags | capi.GM_NO_EXCHANGE, sync=True)
         ranks.append((sp, h, dnz, db))
     for r in range(1, nranks):  # the "NCCL" step: lower interface of r -> upper interface of r-1
@@ -285,6 +287,45 @@ def test_newton_through_the_plugin_matches_oracle_newton(gm, gpu_lib, n, bc, N):
         op.close()
     assert ref.f_converged and got.f_converged
     assert got.iterations == ref.iterations and got.f_calls == ref.f_calls
+    assert np.max(np.abs(got.x - ref.x)) <= 1e-10 * max(1.0, np.max(np.abs(ref.x)))
+
+
+def test_newton_configs_1_and_study1_through_the_plugin(gm, gpu_lib):
+    """north_star: 'Newton converges in the same iteration count with fields within 1e-10' on the reference's own runs:
+    config 1 (examples/simple.jl: 50x50, Pr=0.7, Ra=1e3, n=1, Newton + BackTracking) and the study-1 mesh whose Nusselt
+    number the reference ships (examples/study1/conv_study_square.csv:2: 62x62 wave BCs, n=0.6, Nu_bot_avg =
+    6.670431887977048) -- reproduced through the GPU operator, not only through the oracle."""
+    from orc_operator import OracleOperator
+    for N, bc, prm, nu in ((50, cases.SIMPLE, dict(Pr=0.7, Ra=1e3, n=1.0), None),
+                           (62, cases.WAVE, dict(Pr=100.0, Ra=1e4, n=0.6), 6.670431887977048)):
+        sp = cases.cart(N, bc=bc)
+        ref = gm.solver.newton(OracleOperator(sp, **prm), np.zeros(sp.n_total), ftol=1e-8, xtol=1e-50, iterations=60)
+        op = gm.operator.B200FEOperator(sp, **prm)
+        try:
+            got = gm.solver.newton(op, np.zeros(sp.n_total), ftol=1e-8, xtol=1e-50, iterations=60)
+        finally:
+            op.close()
+        assert ref.f_converged and got.f_converged
+        assert got.iterations == ref.iterations and got.f_calls == ref.f_calls and got.g_calls == ref.g_calls
+        assert np.max(np.abs(got.x - ref.x)) <= 1e-10 * max(1.0, np.max(np.abs(ref.x)))
+        if nu is not None:
+            assert abs(gm.solver.nu_bot_avg(sp, got.x) - nu) <= 1e-12 * nu
+
+
+def test_trust_region_through_the_plugin(gm, gpu_lib):
+    """examples/validation-basak/basak.jl:20-26 drives NLsolve's trust-region method: same driver on the GPU operator and on
+    the oracle -> same accepted / rejected steps, same fields."""
+    from orc_operator import OracleOperator
+    sp = cases.cart(20, bc=cases.SIMPLE)
+    prm = dict(Pr=0.7, Ra=1e3, n=1.0)
+    ref = gm.solver.trust_region(OracleOperator(sp, **prm), np.zeros(sp.n_total), ftol=1e-8, xtol=1e-50, iterations=200)
+    op = gm.operator.B200FEOperator(sp, **prm)
+    try:
+        got = gm.solver.trust_region(op, np.zeros(sp.n_total), ftol=1e-8, xtol=1e-50, iterations=200)
+    finally:
+        op.close()
+    assert ref.f_converged and got.f_converged
+    assert (got.iterations, got.f_calls, got.g_calls) == (ref.iterations, ref.f_calls, ref.g_calls)
     assert np.max(np.abs(got.x - ref.x)) <= 1e-10 * max(1.0, np.max(np.abs(ref.x)))
 
 
