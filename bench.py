@@ -92,8 +92,12 @@ def build_problem(N, bc=TURAN):
 
 
 def algorithmic_bytes(sp, nnz):
-    """8*nnz + 8*n (read x) + 8*n (write b) + 4*30*ncells (cell-dof ids); geometry implicit."""
-    return 8 * nnz + 16 * sp.n_total + 4 * 30 * sp.model.ncells
+    """8*nnz + 8*n (read x) + 8*n (write b) + 4*ld*ncells (cell-dof ids); geometry implicit on Cartesian
+    meshes, + 16*nverts + 4*nv*ncells (coordinates, cell->vertex) otherwise."""
+    m = sp.model
+    ld = 3 * sp.ref.nn + 3
+    geo = 0 if m.cartesian else 16 * m.nverts + 4 * sp.ref.nv * m.ncells
+    return 8 * nnz + 16 * sp.n_total + 4 * ld * m.ncells + geo
 
 
 def cpu_pass(N, prm, passes, threads=None):
@@ -142,6 +146,9 @@ def run_reference(args, prm):
 
 
 def workload_name(args):
+    if args.mesh_type == "tri":
+        return ("unit square split into 2x%dx%d jittered triangles (fixed diagonal), turan BCs, Pr=100 Ra=1e5 n=%g, iterate splitmix64(seed=1234)"
+                % (args.mesh, args.mesh, args.n))
     return "cartesian %dx%d quads, turan BCs, Pr=100 Ra=1e5 n=%g, iterate splitmix64(seed=1234)" % (args.mesh, args.mesh, args.n)
 
 
@@ -153,6 +160,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mesh", type=int, default=0, help="cells per side (default 2048 on 1 GPU)")
     ap.add_argument("--power-index", dest="n", type=float, default=0.0, help="power-law index n (default 0.6; 1.4 for N>1)")
+    ap.add_argument("--mesh-type", default="quad", choices=["quad", "tri"], help="tri: generic (scatter) path on a triangle mesh of 2*mesh^2 cells, 1 GPU")
     ap.add_argument("--layout", default="csc", choices=["csc", "csr"])
     ap.add_argument("--path", default="auto", choices=["auto", "scatter", "cart"])
     ap.add_argument("--kernel", default="auto", choices=["auto", "mma", "gath", "gath1", "sweep"], help="structured-path kernel generation (A/B)")
@@ -165,6 +173,8 @@ def main():
     ap.add_argument("--no-verify", action="store_true", help="skip the sampled row-oracle check (outside the timed region)")
     ap.add_argument("--verify-rows", type=int, default=2000, help="random major dofs checked besides the structural ones")
     args = ap.parse_args()
+    if args.mesh == 0 and args.mesh_type == "tri":
+        args.mesh = 1024  # 2.1 M triangles
     if args.mesh == 0:
         # config 5 of BASELINE.json: 4096^2, n=1.4 -- the mesh the metric / target is quoted on; it fits one B200
         # (147 GB), so N = 1, 2, 4, 8 is one strong-scaling series.  Config 4: --mesh 2048 --power-index 0.6.
@@ -192,7 +202,13 @@ def main():
     # N=1: the whole mesh on one GPU.  N>1: owner-computes row blocks, one block per rank,
     # interface rows summed with NCCL send/recv inside gm_assemble_device.
     t0 = time.perf_counter()
-    model = gm.fe.CartesianModel((0, 1, 0, 1), (args.mesh, args.mesh))
+    if args.mesh_type == "tri":
+        if world > 1:
+            raise SystemExit("bench.py: the triangle (scatter) path runs on one GPU")
+        model = gm.fe.square_tri_model(args.mesh, jitter=0.2, seed=3)
+        args.no_cpu = True   # (the CPU baseline leg is defined on the quad workload)
+    else:
+        model = gm.fe.CartesianModel((0, 1, 0, 1), (args.mesh, args.mesh))
     if world > 1:
         sp = gm.fe.build_rank_spaces(model, TURAN["V"], TURAN["Ttags"], TURAN["Texpr"], rank, world)
     else:

@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -380,11 +381,51 @@ done:
   return rc;
 }
 
+// GM_CHECK_FINITE: device scan of the outputs (both entry points); err[0] = 1 + kind (0 nzval, 1 residual), err64[1] = first index seen
+__global__ void k_check_finite(const double *__restrict__ v, int64_t n, int kind, unsigned long long *__restrict__ err) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    if (!isfinite(v[i]) && atomicCAS(&err[0], 0ull, (unsigned long long)(1 + kind)) == 0ull) err[1] = (unsigned long long)i;
+}
+static int gm_check_finite(gm_handle *h, const double *d_nz, const double *d_b) {
+  unsigned long long *err = nullptr, herr[2] = {0, 0};
+  GM_CUDA(cudaMalloc(&err, 16));
+  GM_CUDA(cudaMemsetAsync(err, 0, 16, h->stream));
+  if (d_nz) k_check_finite<<<h->num_sms * 8, 256, 0, h->stream>>>(d_nz, h->nnz, 0, err);
+  if (d_b) k_check_finite<<<h->num_sms * 8, 256, 0, h->stream>>>(d_b, h->n_total, 1, err);
+  cudaError_t e = cudaMemcpyAsync(herr, err, 16, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(err);
+  if (e != cudaSuccess) { gm_set_error("gm_check_finite: %s", cudaGetErrorString(e)); return GM_ERR_CUDA; }
+  if (herr[0]) {
+    gm_set_error("non-finite %s entry at index %llu", herr[0] == 1 ? "nzval" : "residual", herr[1]);
+    return GM_ERR_NONFINITE;
+  }
+  return GM_OK;
+}
+
+// The scatter kernels read reference tables and parameters from ONE __constant__ block per device (c_gm).  Handles on the
+// same device run on their own streams, so an upload must not overtake the kernels of the handle that used the block last:
+// every upload first makes its stream wait for an event recorded after that handle's last scatter launch.
+struct GmConstUse { cudaEvent_t ev = nullptr; bool used = false; };
+static GmConstUse g_const_use[64];
+static std::mutex g_const_mutex;
+
 static int gm_upload_const(gm_handle *h) {
   GmConst &c = h->hc;
   c.Pr = h->prm.Pr; c.Ra = h->prm.Ra; c.n = h->prm.n; c.reg = h->prm.reg;
   c.gx = h->prm.gx; c.gy = h->prm.gy; c.jac_scaling = h->prm.jac_scaling;
+  std::lock_guard<std::mutex> lock(g_const_mutex);
+  GmConstUse &u = g_const_use[h->dev & 63];
+  if (!u.ev) GM_CUDA(cudaEventCreateWithFlags(&u.ev, cudaEventDisableTiming));
+  if (u.used) GM_CUDA(cudaStreamWaitEvent(h->stream, u.ev, 0));
   GM_CUDA(cudaMemcpyToSymbolAsync(c_gm, &c, sizeof(GmConst), 0, cudaMemcpyHostToDevice, h->stream));
+  return GM_OK;
+}
+static int gm_const_release(gm_handle *h) {  // after the last kernel that reads c_gm has been launched
+  std::lock_guard<std::mutex> lock(g_const_mutex);
+  GmConstUse &u = g_const_use[h->dev & 63];
+  GM_CUDA(cudaEventRecord(u.ev, h->stream));
+  u.used = true;
   return GM_OK;
 }
 
@@ -393,10 +434,12 @@ static int gm_run(gm_handle *h, const double *d_x, double *d_nz, double *d_b, ui
   if ((flags & GM_JACOBIAN) && !d_nz) { gm_set_error("gm_assemble: GM_JACOBIAN without nzval"); return GM_ERR_ARG; }
   if ((flags & GM_RESIDUAL) && !d_b) { gm_set_error("gm_assemble: GM_RESIDUAL without resid"); return GM_ERR_ARG; }
   if (!(flags & (GM_JACOBIAN | GM_RESIDUAL))) { gm_set_error("gm_assemble: nothing to do"); return GM_ERR_ARG; }
+  if (h->active_path == GM_PATH_CART) return gm_cart_run(h, d_x, d_nz, d_b, flags, launches);  // (parameters travel as kernel arguments)
   int rc = gm_upload_const(h);
   if (rc) return rc;
-  if (h->active_path == GM_PATH_CART) return gm_cart_run(h, d_x, d_nz, d_b, flags, launches);
-  return gm_launch_scatter(h, d_x, d_nz, d_b, flags, launches);
+  rc = gm_launch_scatter(h, d_x, d_nz, d_b, flags, launches);
+  if (rc) return rc;
+  return gm_const_release(h);
 }
 
 extern "C" int gm_assemble_device(gm_handle *h, const double *d_x, double *d_nzval, double *d_resid, uint32_t flags,
@@ -414,6 +457,7 @@ extern "C" int gm_assemble_device(gm_handle *h, const double *d_x, double *d_nzv
   h->times.h2d_bytes = h->times.d2h_bytes = 0;
   h->times.kernel_ms = h->times.exchange_ms = -1.0;  // filled by gm_timing once the events have completed
   h->times_pending = true;
+  if (flags & GM_CHECK_FINITE) return gm_check_finite(h, (flags & GM_JACOBIAN) ? d_nzval : nullptr, (flags & GM_RESIDUAL) ? d_resid : nullptr);  // (synchronises)
   if (sync) GM_CUDA(cudaStreamSynchronize(h->stream));
   return GM_OK;
 }
@@ -440,6 +484,10 @@ extern "C" int gm_assemble(gm_handle *h, const double *x, double *nzval, double 
   int rc = gm_run(h, h->d_x, jac ? h->d_nz : nullptr, res ? h->d_b : nullptr, flags, &launches);
   if (rc) return rc;
   GM_CUDA(cudaEventRecord(h->ev[2], h->stream));
+  if (flags & GM_CHECK_FINITE) {  // scanned on the device, before the copies
+    rc = gm_check_finite(h, jac ? h->d_nz : nullptr, res ? h->d_b : nullptr);
+    if (rc) return rc;
+  }
   if (jac) GM_CUDA(cudaMemcpyAsync(nzval, h->d_nz, sizeof(double) * (size_t)h->nnz, cudaMemcpyDeviceToHost, h->stream));
   if (res) GM_CUDA(cudaMemcpyAsync(resid, h->d_b, sizeof(double) * (size_t)h->n_total, cudaMemcpyDeviceToHost, h->stream));
   GM_CUDA(cudaEventRecord(h->ev[3], h->stream));
@@ -452,11 +500,6 @@ extern "C" int gm_assemble(gm_handle *h, const double *x, double *nzval, double 
   h->times.launches = launches;
   h->times.h2d_bytes = 8 * h->n_total;
   h->times.d2h_bytes = (jac ? 8 * h->nnz : 0) + (res ? 8 * h->n_total : 0);
-  if (flags & GM_CHECK_FINITE) {
-    if (res)
-      for (int64_t k = 0; k < h->n_total; ++k)
-        if (!isfinite(resid[k])) { gm_set_error("gm_assemble: non-finite residual entry %lld", (long long)k); return GM_ERR_NONFINITE; }
-  }
   return GM_OK;
 }
 

@@ -549,6 +549,7 @@ __global__ void __launch_bounds__(MM_NT, 2) k_mma(MmArgs args) {
     uint4 recx[2][2];
     auto fetch_records = [&](int X) {
       const bool okL = X > 0, okR = X < a.nx;
+      int cl[4];
 #pragma unroll
       for (int sl = 0; sl < 2; ++sl) {
         const uint32_t sf = (okL && okR) ? selfast[sl] : (select(s.out[tile8[sl] + 2 * j], okL, okR) | (select(s.out[tile8[sl] + 2 * j + 1], okL, okR) << 16));
@@ -557,11 +558,16 @@ __global__ void __launch_bounds__(MM_NT, 2) k_mma(MmArgs args) {
           const uint32_t se = (sf >> (16 * c)) & 0xFFFFu;
           selx[sl][c] = se;
           const int cx = X - (int)((se >> 11) & 1);
-          const int cl = (se >> 15) ? s.cls[cx & 7][(se >> 7) & 15] : cls0;
-          uint4 r = s.prec[se & 127];
-          if (cl != cls0) r = GA_LDG(reinterpret_cast<const uint4 *>(a.ptab) + ((int64_t)cl * 81 + (se & 127)));
-          recx[sl][c] = r;
+          cl[2 * sl + c] = (se >> 15) ? s.cls[cx & 7][(se >> 7) & 15] : cls0;  // (four independent class lookups ...)
         }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) recx[k >> 1][k & 1] = s.prec[selx[k >> 1][k & 1] & 127];  // (... four independent record loads)
+      if (cl[0] != cls0 || cl[1] != cls0 || cl[2] != cls0 || cl[3] != cls0) {  // rare: a cell of another rank class (mesh boundary)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (cl[k] != cls0)
+            recx[k >> 1][k & 1] = GA_LDG(reinterpret_cast<const uint4 *>(a.ptab) + ((int64_t)cl[k] * 81 + (selx[k >> 1][k & 1] & 127)));
       }
     };
 

@@ -58,7 +58,7 @@ enum gm_layout { GM_LAYOUT_CSC = 0, GM_LAYOUT_CSR = 1 };
 /* gm_assemble flags */
 #define GM_JACOBIAN 1u     /* jacobian!(A, op, x)   */
 #define GM_RESIDUAL 2u     /* residual!(b, op, x)   */
-#define GM_CHECK_FINITE 4u /* scan outputs for NaN/Inf on the device */
+#define GM_CHECK_FINITE 4u /* scan nzval and the residual for NaN/Inf on the device (both entry points; the device one then synchronises) */
 #define GM_NO_EXCHANGE 8u  /* multi-GPU: skip the NCCL interface-row sum (caller moves the packed buffers) */
 
 /* Numeric kernels */

@@ -103,6 +103,65 @@ def test_error_paths(gm, gpu_lib):
     h.close()
 
 
+@pytest.mark.parametrize("path", ["scatter", "cart"])
+def test_check_finite_flag_scans_on_the_device(gm, gpu_lib, path):
+    """GM_CHECK_FINITE: a NaN in the iterate must surface as GM_ERR_NONFINITE (-6) from both entry points, for nzval and for
+    the residual; a clean iterate passes."""
+    import torch
+    capi = gm.capi
+    sp = cases.cart(9, 6, bc=cases.TURAN)
+    h = capi.Handle(sp, path=capi.GM_PATH_SCATTER if path == "scatter" else capi.GM_PATH_CART)
+    try:
+        h.set_params(Pr=100.0, Ra=1e5, n=0.6)
+        nnz = h.pattern()
+        x = fe.splitmix_iterate(sp.n_total, 1234)
+        nz, b = np.empty(nnz), np.empty(sp.n_total)
+        h.assemble(x, nz, b, flags=capi.GM_JACOBIAN | capi.GM_RESIDUAL | capi.GM_CHECK_FINITE)
+        bad = x.copy()
+        bad[sp.n_total // 3] = np.nan
+        for fl in (capi.GM_JACOBIAN, capi.GM_RESIDUAL):
+            with pytest.raises(capi.GmError) as ei:
+                h.assemble(bad, nz if fl == capi.GM_JACOBIAN else None, b if fl == capi.GM_RESIDUAL else None, flags=fl | capi.GM_CHECK_FINITE)
+            assert ei.value.code == -6
+        dx, dnz, db = torch.from_numpy(bad).cuda(), torch.empty(nnz, dtype=torch.float64, device="cuda"), torch.empty(sp.n_total, dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        with pytest.raises(capi.GmError) as ei:
+            h.assemble_device(dx.data_ptr(), dnz.data_ptr(), db.data_ptr(), capi.GM_JACOBIAN | capi.GM_RESIDUAL | capi.GM_CHECK_FINITE, sync=False)
+        assert ei.value.code == -6
+    finally:
+        h.close()
+
+
+def test_two_handles_one_process_interleaved(gm, gpu_lib):
+    """'distinct handles are independent' (include/gemotion_b200.h): two handles with different parameters and paths in one
+    process, assemblies issued back to back without synchronisation in between, each on its own stream."""
+    import torch
+    capi = gm.capi
+    spa, spb = cases.cart(24, 16, bc=cases.TURAN), cases.spaces(fe.square_tri_model(10, jitter=0.2, seed=4), cases.TURAN)
+    pa, pb = dict(Pr=100.0, Ra=1e5, n=0.6), dict(Pr=0.7, Ra=1e3, n=1.0)
+    items = []
+    for sp, prm, path in ((spa, pa, capi.GM_PATH_SCATTER), (spb, pb, capi.GM_PATH_SCATTER), (spa, pb, capi.GM_PATH_CART)):
+        h = capi.Handle(sp, path=path)
+        h.set_params(**prm)
+        nnz = h.pattern()
+        x = fe.splitmix_iterate(sp.n_total, 1234)
+        items.append((sp, prm, h, torch.from_numpy(x).cuda(), torch.empty(nnz, dtype=torch.float64, device="cuda"),
+                      torch.empty(sp.n_total, dtype=torch.float64, device="cuda"), x))
+    torch.cuda.synchronize()
+    fl = capi.GM_JACOBIAN | capi.GM_RESIDUAL
+    for _ in range(3):
+        for sp, prm, h, dx, dnz, db, x in items:
+            h.assemble_device(dx.data_ptr(), dnz.data_ptr(), db.data_ptr(), fl, sync=False)
+    for sp, prm, h, dx, dnz, db, x in items:
+        h.timing()  # waits for the handle's last event
+        orc = Oracle(sp, **prm)
+        optr, oidx = orc.pattern("csc")
+        onz, ob = orc.assemble(x, "csc")
+        assert cases.block_scaled_err(dnz.cpu().numpy(), onz, cases.nz_blocks(sp, optr, oidx)) <= TOL
+        assert cases.block_scaled_err(db.cpu().numpy(), ob, cases.res_blocks(sp)) <= TOL
+        h.close()
+
+
 CART_CASES = [
     ("8x8_simple", 8, 8, cases.SIMPLE), ("13x7_turan", 13, 7, cases.TURAN), ("1x1", 1, 1, cases.TURAN),
     ("2x3_wave", 2, 3, cases.WAVE), ("20x19_turan", 20, 19, cases.TURAN), ("70x17_simple", 70, 17, cases.SIMPLE),
