@@ -91,20 +91,26 @@ static inline int gm_gath_chunk(int nx, int nstrips, int nsm) {
 
 // x-chunk length of k_mma (a run-time argument).  A CTA sweeps `warm` warm-up columns + one chunk; `slots` CTAs are
 // resident at a time (2 per SM), so a launch of nstrips x nchunks CTAs takes ceil(nstrips * nchunks / slots) waves of
-// (chunk + warm) column steps.  Picks the chunk in [96, 768] that minimises that estimate (the fixed 256 / 128 choice of
-// k_gath left the last wave 27 % full on 8 GPUs: 65 strips x 17 chunks on 296 slots).
+// (chunk + warm) column steps.  Picks the chunk in [96, 768] that minimises that estimate among the chunkings with at
+// least 12 waves (else 8, else any): measured on 4096^2 (profiles/r02_chunk_sweep.txt), few long waves lose more than the
+// warm-up of short chunks costs -- the CTAs of a wave start in lock-step and their write-out bursts collide, and the tail
+// of the last wave is a larger share -- e.g. 8 GPUs (65 strips): 228 columns / 4 waves 5.14 ms, 114 columns / 8 waves
+// 4.83 ms; 4 GPUs: 456 / 4 waves 10.44 ms, 152 / 12 waves 9.48 ms; 1 GPU (513 strips, >= 30 waves): 96 -> 37.6, 216 -> 37.0 ms.
 static inline int gm_mma_chunk(int nx, int nstrips, int slots, int warm) {
-  long long best = -1;
-  int best_ch = 256;
-  for (int pass = 0; pass < 2 && best < 0; ++pass)  // first only chunkings with at least four waves (load balance, and the
-    for (int ch = 96; ch <= 768; ch += 4) {          // interface strip of a multi-GPU rank finishes early), then any
+  const int min_waves[3] = {12, 8, 1};
+  for (int pass = 0; pass < 3; ++pass) {
+    long long best = -1;
+    int best_ch = 256;
+    for (int ch = 96; ch <= 768; ch += 4) {
       const long long nchunks = (nx + 1 + ch - 1) / ch;
       const long long waves = (nchunks * nstrips + slots - 1) / slots;
-      if (pass == 0 && waves < 4) continue;
+      if (waves < min_waves[pass]) continue;
       const long long cost = waves * (ch + warm);
       if (best < 0 || cost * 200 < best * 199) { best = cost; best_ch = ch; }  // (a longer chunk must win by 0.5 %)
     }
-  return best_ch;
+    if (best >= 0) return best_ch;
+  }
+  return 256;
 }
 
 // Pair-major copy of the class tables for k_gath: record [class][major node M][minor node m] holds the 9
