@@ -24,7 +24,8 @@ GM_KERNEL_AUTO, GM_KERNEL_MMA, GM_KERNEL_GATH, GM_KERNEL_GATH1, GM_KERNEL_SWEEP 
 EXPORTS = ["gm_version", "gm_last_error", "gm_create", "gm_destroy", "gm_set_params", "gm_pattern",
            "gm_get_pattern", "gm_get_rows", "gm_assemble", "gm_assemble_device", "gm_host_register", "gm_host_unregister",
            "gm_set_stream", "gm_timing", "gm_info", "gm_nccl_unique_id", "gm_comm_init",
-           "gm_iface_count", "gm_iface_pack", "gm_iface_unpack_add"]
+           "gm_iface_count", "gm_iface_pack", "gm_iface_unpack_add",
+           "gm_post_create", "gm_post_sizes", "gm_post_get_pattern", "gm_post_assemble", "gm_post_entropy"]
 
 
 class GmError(RuntimeError):
@@ -51,6 +52,18 @@ class gm_desc(C.Structure):
         ("cell_begin", C.c_int64), ("ncells_global", C.c_int64),
         ("ghost_lo", C.c_int32), ("ghost_hi", C.c_int32),
         ("kernel", C.c_int32), ("xchunk", C.c_int32),
+    ]
+
+
+class gm_post_desc(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32), ("nq2", C.c_int32), ("nq4", C.c_int32),
+        ("cell_dofs_psi", C.c_void_p), ("n_free_psi", C.c_int64), ("n_diri_psi", C.c_int64), ("diri_psi", C.c_void_p),
+        ("cell_dofs_pi", C.c_void_p), ("n_free_pi", C.c_int64), ("n_diri_pi", C.c_int64), ("diri_pi", C.c_void_p),
+        ("w2", C.c_void_p), ("g2", C.c_void_p), ("dg2", C.c_void_p), ("phi2", C.c_void_p), ("dphi2", C.c_void_p),
+        ("w4", C.c_void_p), ("g4", C.c_void_p), ("dg4", C.c_void_p), ("phi4", C.c_void_p), ("dphi4", C.c_void_p),
+        ("dphi_nodes", C.c_void_p), ("dg_nodes", C.c_void_p),
+        ("cell_nodes", C.c_void_p), ("n_nodes", C.c_int64),
     ]
 
 
@@ -221,6 +234,45 @@ class Handle:
         """Device pointers (ints)."""
         _check(lib().gm_assemble_device(self._h, C.c_void_p(d_x), C.c_void_p(d_nz or 0), C.c_void_p(d_b or 0),
                                         C.c_uint32(flags), C.c_int32(1 if sync else 0)))
+
+    # ---- post-processing assemblies (Solver.jl:197-292)
+    def post_create(self, sp, psi_space, pi_space, tabs):
+        """`psi_space` / `pi_space`: fe.P1Space of the stream / heat function; `tabs`: fe.PostTables."""
+        c = np.ascontiguousarray
+        k = dict(dpsi=c(psi_space.cell_dofs, dtype=np.int32), dpi=c(pi_space.cell_dofs, dtype=np.int32),
+                 vpsi=c(psi_space.diri_values, dtype=np.float64), vpi=c(pi_space.diri_values, dtype=np.float64),
+                 cn=c(sp.T.cell_nodes, dtype=np.int32), dpn=c(tabs.dphi_n), dgn=c(tabs.dg_n))
+        for r in (0, 1):
+            for nm, arr in (("w", tabs.w), ("g", tabs.g), ("dg", tabs.dg), ("phi", tabs.phi), ("dphi", tabs.dphi)):
+                k["%s%d" % (nm, r)] = c(arr[r], dtype=np.float64)
+        d = gm_post_desc()
+        d.struct_size = C.sizeof(gm_post_desc)
+        d.nq2, d.nq4 = tabs.w[0].size, tabs.w[1].size
+        d.cell_dofs_psi, d.n_free_psi, d.n_diri_psi, d.diri_psi = _p(k["dpsi"]), psi_space.n_free, psi_space.n_diri, (_p(k["vpsi"]) if psi_space.n_diri else None)
+        d.cell_dofs_pi, d.n_free_pi, d.n_diri_pi, d.diri_pi = _p(k["dpi"]), pi_space.n_free, pi_space.n_diri, (_p(k["vpi"]) if pi_space.n_diri else None)
+        d.w2, d.g2, d.dg2, d.phi2, d.dphi2 = _p(k["w0"]), _p(k["g0"]), _p(k["dg0"]), _p(k["phi0"]), _p(k["dphi0"])
+        d.w4, d.g4, d.dg4, d.phi4, d.dphi4 = _p(k["w1"]), _p(k["g1"]), _p(k["dg1"]), _p(k["phi1"]), _p(k["dphi1"])
+        d.dphi_nodes, d.dg_nodes = _p(k["dpn"]), _p(k["dgn"])
+        d.cell_nodes, d.n_nodes = _p(k["cn"]), int(sp.T.node_coords.shape[0])
+        _check(lib().gm_post_create(self._h, C.byref(d)))
+        self._post_nodes = d.n_nodes
+
+    def post_assemble(self, which, x):
+        """(A scipy csc, b) of the stream (0) / heat (1) function problem at the solution x."""
+        import scipy.sparse as sps
+        n, nnz = C.c_int64(), C.c_int64()
+        _check(lib().gm_post_sizes(self._h, C.c_int32(which), C.byref(n), C.byref(nnz)))
+        ptr, idx = np.empty(n.value + 1, dtype=np.int64), np.empty(nnz.value, dtype=np.int64)
+        _check(lib().gm_post_get_pattern(self._h, C.c_int32(which), _p(ptr), _p(idx), C.c_int32(0)))
+        nz, b = np.empty(nnz.value), np.empty(n.value)
+        _check(lib().gm_post_assemble(self._h, C.c_int32(which), _p(np.ascontiguousarray(x, dtype=np.float64)), _p(nz), _p(b)))
+        return sps.csc_matrix((nz, idx, ptr), shape=(n.value, n.value)), b
+
+    def post_entropy(self, x):
+        """(Sth nodal, Sfl nodal, Sth_tot, Sfl_tot, Be_avg)."""
+        sth, sfl, tot = np.empty(self._post_nodes), np.empty(self._post_nodes), np.empty(3)
+        _check(lib().gm_post_entropy(self._h, _p(np.ascontiguousarray(x, dtype=np.float64)), _p(sth), _p(sfl), _p(tot)))
+        return sth, sfl, float(tot[0]), float(tot[1]), float(tot[2])
 
     # ---- multi-GPU row blocks
     def comm_init(self, id128: bytes):

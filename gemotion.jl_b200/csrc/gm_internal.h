@@ -60,6 +60,7 @@ struct gm_handle {
   int active_path = GM_PATH_SCATTER;
   void *cart = nullptr;
   void *multi = nullptr;  // gm_multi (row-block interface exchange)
+  void *post = nullptr;   // gm_post (post-processing assemblies, gm_post.cuh)
   // staging for the host API
   double *d_x = nullptr, *d_b = nullptr, *d_nz = nullptr;
   int64_t d_nz_cap = 0;

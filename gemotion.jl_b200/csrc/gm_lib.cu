@@ -14,6 +14,7 @@
 #include "gm_scatter.cuh"
 #include "gm_multi.cuh"
 #include "gm_cart.cuh"
+#include "gm_post.cuh"
 
 static thread_local char g_err[1024] = "";
 
@@ -239,6 +240,7 @@ extern "C" void gm_destroy(gm_handle *h) {
   if (!h) return;
   cudaSetDevice(h->dev);
   gm_multi_destroy(h);
+  gm_post_destroy(h);
   gm_cart_destroy(h);
   cudaFree(h->gdofs); cudaFree(h->dvals); cudaFree(h->coords); cudaFree(h->cellv);
   cudaFree(h->ptr); cudaFree(h->idx); cudaFree(h->rank); cudaFree(h->color_cells);
@@ -596,4 +598,130 @@ extern "C" int gm_iface_unpack_add(gm_handle *h, double *d_nzval, double *d_resi
   if (rc) return rc;
   GM_CUDA(cudaStreamSynchronize(h->stream));
   return GM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// post-processing assemblies (gm_post.cuh)
+// ------------------------------------------------------------------------------------------
+extern "C" int gm_post_create(gm_handle *h, const gm_post_desc *d) {
+  if (!h || !d) { gm_set_error("gm_post_create: null argument"); return GM_ERR_ARG; }
+  if (d->struct_size != (int32_t)sizeof(gm_post_desc)) { gm_set_error("gm_post_create: gm_post_desc size mismatch"); return GM_ERR_ARG; }
+  if (h->d.ghost_lo || h->d.ghost_hi) { gm_set_error("gm_post_create: post-processing runs on a single-GPU handle"); return GM_ERR_ARG; }
+  if (!d->cell_dofs_psi || !d->cell_dofs_pi || !d->w2 || !d->g2 || !d->dg2 || !d->phi2 || !d->dphi2 || !d->w4 || !d->g4 || !d->dg4 || !d->phi4 ||
+      !d->dphi4 || !d->dphi_nodes || !d->dg_nodes || !d->cell_nodes || d->nq2 <= 0 || d->nq4 <= 0 || d->n_nodes <= 0) {
+    gm_set_error("gm_post_create: missing table");
+    return GM_ERR_ARG;
+  }
+  GM_CUDA(cudaSetDevice(h->dev));
+  gm_post_destroy(h);
+  gm_post *p = new (std::nothrow) gm_post();
+  if (!p) return GM_ERR_OOM;
+  h->post = p;
+  const int nn = h->nn, nv = h->nv;
+  int rc = GM_OK;
+  for (int r = 0; r < 2 && rc == GM_OK; ++r) {
+    const int nq = r == 0 ? d->nq2 : d->nq4;
+    p->nq[r] = nq;
+    const double *src[5] = {r == 0 ? d->w2 : d->w4, r == 0 ? d->g2 : d->g4, r == 0 ? d->dg2 : d->dg4, r == 0 ? d->phi2 : d->phi4, r == 0 ? d->dphi2 : d->dphi4};
+    const size_t cnt[5] = {(size_t)nq, (size_t)nq * nv, (size_t)nq * nv * 2, (size_t)nq * nn, (size_t)nq * nn * 2};
+    std::vector<double> t;
+    for (int k = 0; k < 5; ++k) t.insert(t.end(), src[k], src[k] + cnt[k]);
+    rc = gm_post_up(&p->tab[r], t.data(), t.size());
+  }
+  if (rc == GM_OK) {
+    std::vector<double> t(d->dphi_nodes, d->dphi_nodes + (size_t)nn * nn * 2);
+    t.insert(t.end(), d->dg_nodes, d->dg_nodes + (size_t)nn * nv * 2);
+    rc = gm_post_up(&p->ntab, t.data(), t.size());
+  }
+  if (rc == GM_OK) rc = gm_post_space_build(h, p->sp[0], d->cell_dofs_psi, d->n_free_psi, d->n_diri_psi, d->diri_psi);
+  if (rc == GM_OK) rc = gm_post_space_build(h, p->sp[1], d->cell_dofs_pi, d->n_free_pi, d->n_diri_pi, d->diri_pi);
+  if (rc == GM_OK) {
+    p->n_nodes = d->n_nodes;
+    rc = gm_post_up(&p->cell_nodes, d->cell_nodes, (size_t)(h->ncells * nn));
+    std::vector<int32_t> last((size_t)d->n_nodes, 0);
+    for (int64_t k = 0; k < h->ncells * nn; ++k) last[d->cell_nodes[k]] = (int32_t)k;  // ascending: the last cell wins
+    if (rc == GM_OK) rc = gm_post_up(&p->node_last, last.data(), last.size());
+  }
+  if (rc == GM_OK) {
+    const size_t per = (size_t)std::max(nv * nv + nv, 2 * nn);
+    cudaError_t e = cudaMalloc(&p->cellbuf, sizeof(double) * per * (size_t)h->ncells);
+    if (e != cudaSuccess) { gm_set_error("gm_post_create: %s", cudaGetErrorString(e)); rc = GM_ERR_OOM; }
+  }
+  if (rc != GM_OK) gm_post_destroy(h);
+  return rc;
+}
+
+extern "C" int gm_post_sizes(gm_handle *h, int32_t which, int64_t *n, int64_t *nnz) {
+  gm_post *p = h ? (gm_post *)h->post : nullptr;
+  if (!p || which < 0 || which > 1) { gm_set_error("gm_post_sizes: call gm_post_create first / bad problem id"); return GM_ERR_STATE; }
+  if (n) *n = p->sp[which].n;
+  if (nnz) *nnz = p->sp[which].nnz;
+  return GM_OK;
+}
+
+extern "C" int gm_post_get_pattern(gm_handle *h, int32_t which, int64_t *colptr, int64_t *rowval, int32_t index_base) {
+  gm_post *p = h ? (gm_post *)h->post : nullptr;
+  if (!p || which < 0 || which > 1 || !colptr || !rowval) { gm_set_error("gm_post_get_pattern: bad argument"); return GM_ERR_ARG; }
+  const gm_post_space &s = p->sp[which];
+  for (int64_t k = 0; k <= s.n; ++k) colptr[k] = s.hptr[k] + index_base;
+  for (int64_t k = 0; k < s.nnz; ++k) rowval[k] = (int64_t)s.hidx[k] + index_base;
+  return GM_OK;
+}
+
+extern "C" int gm_post_assemble(gm_handle *h, int32_t which, const double *x, double *nzval, double *b) {
+  gm_post *p = h ? (gm_post *)h->post : nullptr;
+  if (!p || which < 0 || which > 1 || !x || !nzval || !b) { gm_set_error("gm_post_assemble: bad argument"); return GM_ERR_ARG; }
+  GM_CUDA(cudaSetDevice(h->dev));
+  gm_post_space &s = p->sp[which];
+  double *d_nz = nullptr, *d_b = nullptr;
+  GM_CUDA(cudaMalloc(&d_nz, sizeof(double) * (size_t)std::max<int64_t>(s.nnz, 1)));
+  GM_CUDA(cudaMalloc(&d_b, sizeof(double) * (size_t)std::max<int64_t>(s.n, 1)));
+  GM_CUDA(cudaMemcpyAsync(h->d_x, x, sizeof(double) * (size_t)h->n_total, cudaMemcpyHostToDevice, h->stream));
+  GmPostArgs a = gm_post_args(h, p, which, h->d_x);
+  a.pdofs = s.dofs; a.pdiri = s.diri;
+  if (which == 0) k_post_cells<0><<<gm_blocks(h->ncells, 128), 128, 0, h->stream>>>(a);
+  else k_post_cells<1><<<gm_blocks(h->ncells, 128), 128, 0, h->stream>>>(a);
+  k_post_gather<<<gm_blocks(s.n, 128), 128, 0, h->stream>>>(s.n, h->nv, s.adjptr, s.adj, s.dofs, s.ptr, s.idx, p->cellbuf, d_nz, d_b);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(nzval, d_nz, sizeof(double) * (size_t)s.nnz, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(b, d_b, sizeof(double) * (size_t)s.n, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_nz); cudaFree(d_b);
+  if (e != cudaSuccess) { gm_set_error("gm_post_assemble: %s", cudaGetErrorString(e)); return GM_ERR_CUDA; }
+  return GM_OK;
+}
+
+extern "C" int gm_post_entropy(gm_handle *h, const double *x, double *sth, double *sfl, double *totals) {
+  gm_post *p = h ? (gm_post *)h->post : nullptr;
+  if (!p || !x || !sth || !sfl || !totals) { gm_set_error("gm_post_entropy: bad argument"); return GM_ERR_ARG; }
+  GM_CUDA(cudaSetDevice(h->dev));
+  double *d_s = nullptr, *d_part = nullptr, *d_tot = nullptr;
+  void *tmp = nullptr;
+  size_t tb = 0;
+  int rc = GM_OK;
+  cudaError_t e = cudaMalloc(&d_s, sizeof(double) * 2 * (size_t)p->n_nodes);
+  if (e == cudaSuccess) e = cudaMalloc(&d_part, sizeof(double) * 2 * (size_t)h->ncells);
+  if (e == cudaSuccess) e = cudaMalloc(&d_tot, 16);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h->d_x, x, sizeof(double) * (size_t)h->n_total, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) {
+    GmPostArgs a = gm_post_args(h, p, 0, h->d_x);
+    k_post_entropy_cells<<<gm_blocks(h->ncells, 128), 128, 0, h->stream>>>(a, p->ntab);
+    k_post_entropy_nodes<<<gm_blocks(p->n_nodes, 256), 256, 0, h->stream>>>(p->n_nodes, p->node_last, p->cellbuf, d_s, d_s + p->n_nodes);
+    k_post_entropy_int<<<gm_blocks(h->ncells, 128), 128, 0, h->stream>>>(a, p->cell_nodes, d_s, d_s + p->n_nodes, d_part);
+    cub::DeviceReduce::Sum(nullptr, tb, d_part, d_tot, h->ncells, h->stream);
+    e = cudaMalloc(&tmp, tb ? tb : 16);
+    if (e == cudaSuccess) {
+      cub::DeviceReduce::Sum(tmp, tb, d_part, d_tot, h->ncells, h->stream);
+      cub::DeviceReduce::Sum(tmp, tb, d_part + h->ncells, d_tot + 1, h->ncells, h->stream);
+      e = cudaGetLastError();
+    }
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(sth, d_s, sizeof(double) * (size_t)p->n_nodes, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(sfl, d_s + p->n_nodes, sizeof(double) * (size_t)p->n_nodes, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(totals, d_tot, 16, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_s); cudaFree(d_part); cudaFree(d_tot); cudaFree(tmp);
+  if (e != cudaSuccess) { gm_set_error("gm_post_entropy: %s", cudaGetErrorString(e)); rc = GM_ERR_CUDA; }
+  else totals[2] = totals[0] / (totals[0] + totals[1]);  // Be_avg (Solver.jl:292)
+  return rc;
 }

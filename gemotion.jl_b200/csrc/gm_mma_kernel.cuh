@@ -35,8 +35,7 @@
 #define MM_NR (MM_QH + 1)            // cell rows of state (one halo row below)
 #define MM_PST (MM_NR * 4)           // doubles per state plane: [cell row][point]
 #define MM_VST 36                    // row stride of the staged iterate values (30 used; k-steps read up to index 32; bank spread)
-#define MM_QSTRIDE 738               // staged doubles per quad row: 15 list slots (728) + pad; = 2 mod 16, so that the eight rows an
-                                     // epilogue store touches start in eight different 8-byte bank pairs (732 mapped rows r and r+4 together)
+#define MM_QSTRIDE 732               // staged doubles per quad row: 15 list slots (728) + pad (738 = 2 mod 16 was tried: more bank conflicts in the epilogue, 113 vs 93 wavefronts per cell)
 #define MM_NMW 4                     // main warps
 #define MM_NAW 4                     // aux warps
 #define MM_NT ((MM_NMW + MM_NAW) * 32)

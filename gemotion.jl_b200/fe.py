@@ -622,3 +622,80 @@ def owned_dofs(sp: Spaces) -> np.ndarray:
     r0, r1, glo, ghi = sp.rows
     mine = _global_ids_of_rows(sp, slice(glo, glo + (r1 - r0)))
     return np.setdiff1d(mine, interface_dofs(sp, 0), assume_unique=True)
+
+
+# --------------------------------------------------------------------------------------
+# post-processing spaces and tables (/root/reference/src/Solver.jl:197-292): P1 stream / heat function spaces,
+# Measure(Ω, 4) for the heat function, nodal gradients for the entropy interpolation
+# --------------------------------------------------------------------------------------
+@dataclasses.dataclass
+class P1Space:
+    """`TestFESpace(model, ReferenceFE(lagrangian, Float64, 1), conformity=:H1, dirichlet_tags=...)` (Solver.jl:200-204,
+    239-245): one dof per vertex; on quads the Q1 basis."""
+    n_free: int
+    n_diri: int
+    cell_dofs: np.ndarray     # [nc, nv] int32 signed 1-based
+    diri_values: np.ndarray   # [n_diri]
+
+
+def build_p1(model: DiscreteModel, diri_tags: Sequence, diri_value: float = 0.0) -> P1Space:
+    tagidx = _face_tag_index(model.vertex_entity, model, diri_tags) if len(diri_tags) else np.full(model.nverts, -1, np.int32)
+    diri = tagidx >= 0
+    signed = np.where(diri, -np.cumsum(diri), np.cumsum(~diri)).astype(np.int32)
+    return P1Space(int((~diri).sum()), int(diri.sum()), np.ascontiguousarray(signed[model.cell_vertices]),
+                   np.full(int(diri.sum()), float(diri_value)))
+
+
+def quadrature(cell_type: int, degree: int):
+    """(points [nq,2], weights [nq]) of Gridap's `Measure(Ω, degree)` on the reference cell for degree 2 and 4.
+    QUAD: tensor Gauss-Legendre with ceil((degree+1)/2) points per direction (x fastest).  TRI degree 4: the 6-point
+    Strang-Fix / Dunavant rule [Gridap ◐: unverified which of its tabulated degree-4 simplex rules is picked]."""
+    if cell_type == QUAD or degree == 2:
+        t = reference_tables(cell_type, degree)
+        return t.qp, t.w
+    if degree == 4:
+        a1, a2 = 0.445948490915965, 0.091576213509771
+        w1, w2 = 0.223381589678011 / 2, 0.109951743655322 / 2
+        qp = np.array([[a1, a1], [1 - 2 * a1, a1], [a1, 1 - 2 * a1], [a2, a2], [1 - 2 * a2, a2], [a2, 1 - 2 * a2]])
+        return qp, np.array([w1, w1, w1, w2, w2, w2])
+    raise ValueError("quadrature degree %d not tabulated" % degree)
+
+
+def vertex_basis(cell_type: int, x: float, y: float):
+    """P1 / Q1 (= geometry) basis values [nv] and reference gradients [nv,2] at one reference point."""
+    if cell_type == QUAD:
+        g = np.array([(1 - x) * (1 - y), x * (1 - y), (1 - x) * y, x * y])
+        dg = np.array([[-(1 - y), -(1 - x)], [(1 - y), -x], [-y, (1 - x)], [y, x]])
+    else:
+        g = np.array([1 - x - y, x, y])
+        dg = np.array([[-1.0, -1.0], [1.0, 0.0], [0.0, 1.0]])
+    return g, dg
+
+
+@dataclasses.dataclass
+class PostTables:
+    """Tabulated bases for the post-processing assemblies: per rule r in (degree 2, degree 4): w[r] [nq], g[r] [nq,nv],
+    dg[r] [nq,nv,2] (vertex basis = geometry basis), phi[r] [nq,nn], dphi[r] [nq,nn,2] (P2 basis); at the nn P2 nodes:
+    dphi_n [nn,nn,2] (P2 gradients), dg_n [nn,nv,2] (geometry gradients)."""
+    w: list
+    g: list
+    dg: list
+    phi: list
+    dphi: list
+    dphi_n: np.ndarray
+    dg_n: np.ndarray
+
+
+def post_tables(cell_type: int) -> PostTables:
+    w, g, dg, phi, dphi = [], [], [], [], []
+    for degree in (2, 4):
+        qp, ww = quadrature(cell_type, degree)
+        w.append(np.ascontiguousarray(ww))
+        g.append(np.array([vertex_basis(cell_type, x, y)[0] for x, y in qp]))
+        dg.append(np.array([vertex_basis(cell_type, x, y)[1] for x, y in qp]))
+        phi.append(np.array([shape_at(cell_type, x, y)[0] for x, y in qp]))
+        dphi.append(np.array([shape_at(cell_type, x, y)[1] for x, y in qp]))
+    nodes = reference_tables(cell_type, 2).nodes
+    dphi_n = np.array([shape_at(cell_type, x, y)[1] for x, y in nodes])
+    dg_n = np.array([vertex_basis(cell_type, x, y)[1] for x, y in nodes])
+    return PostTables(w, g, dg, phi, dphi, dphi_n, dg_n)

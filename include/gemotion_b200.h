@@ -211,6 +211,39 @@ int gm_iface_count(gm_handle *h, int32_t side, int64_t *ndoubles);
 int gm_iface_pack(gm_handle *h, const double *d_nzval, const double *d_resid, double *d_buf, uint32_t flags);
 int gm_iface_unpack_add(gm_handle *h, double *d_nzval, double *d_resid, const double *d_buf, uint32_t flags);
 
+/*
+ * Post-processing assemblies that follow the Newton solve (/root/reference/src/Solver.jl:197-292): the stream function and
+ * heat function problems (AffineFEOperator on a P1 space, Solver.jl:200-210 and 254-273) and the entropy fields
+ * (interpolate + integrals, Solver.jl:281-292).  `which`: 0 = stream function (Measure(Ω,2)), 1 = heat function (Measure(Ω,4)).
+ * Tables are inputs like in gm_desc: in production Gridap supplies them.
+ */
+typedef struct gm_post_desc {
+  int32_t struct_size;
+  int32_t nq2, nq4;                     /* points of Measure(Ω,2) and Measure(Ω,4) */
+  const int32_t *cell_dofs_psi;         /* [ncells*nv] signed 1-based dof ids of the stream-function space (Dirichlet on V_diri_tags) */
+  int64_t n_free_psi, n_diri_psi;
+  const double *diri_psi;               /* [n_diri_psi] (0.0 in the reference) */
+  const int32_t *cell_dofs_pi;          /* same for the heat-function space (Dirichlet on T_natural_tags, or none) */
+  int64_t n_free_pi, n_diri_pi;
+  const double *diri_pi;
+  /* per rule: weights [nq], vertex (= geometry) basis [nq*nv] and reference gradients [nq*nv*2], P2 basis [nq*nn] and gradients [nq*nn*2] */
+  const double *w2, *g2, *dg2, *phi2, *dphi2;
+  const double *w4, *g4, *dg4, *phi4, *dphi4;
+  const double *dphi_nodes;             /* [nn*nn*2] P2 reference gradients at the nn P2 nodes (entropy interpolation) */
+  const double *dg_nodes;               /* [nn*nv*2] geometry gradients at the nodes */
+  const int32_t *cell_nodes;            /* [ncells*nn] 0-based node ids of the P2 H1 space the entropies are interpolated into */
+  int64_t n_nodes;
+} gm_post_desc;
+
+int gm_post_create(gm_handle *h, const gm_post_desc *desc);
+/* sizes of problem `which`; pattern of its CSC matrix (colptr n+1, rowval nnz) */
+int gm_post_sizes(gm_handle *h, int32_t which, int64_t *n, int64_t *nnz);
+int gm_post_get_pattern(gm_handle *h, int32_t which, int64_t *colptr, int64_t *rowval, int32_t index_base);
+/* assembles matrix values (nnz) and right-hand side (n) of problem `which` at the solution x (host arrays) */
+int gm_post_assemble(gm_handle *h, int32_t which, const double *x, double *nzval, double *b);
+/* nodal entropy fields sth, sfl [n_nodes] and totals = {Sth_tot, Sfl_tot, Be_avg} (Solver.jl:281-292) */
+int gm_post_entropy(gm_handle *h, const double *x, double *sth, double *sfl, double *totals);
+
 #ifdef __cplusplus
 }
 #endif
