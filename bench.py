@@ -160,9 +160,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mesh", type=int, default=0, help="cells per side (default 2048 on 1 GPU)")
     ap.add_argument("--power-index", dest="n", type=float, default=0.0, help="power-law index n (default 0.6; 1.4 for N>1)")
-    ap.add_argument("--mesh-type", default="quad", choices=["quad", "tri"], help="tri: generic (scatter) path on a triangle mesh of 2*mesh^2 cells, 1 GPU")
+    ap.add_argument("--mesh-type", default="quad", choices=["quad", "tri"], help="tri: generic path (gather; --path scatter for the first generation) on a triangle mesh of 2*mesh^2 cells, 1 GPU")
     ap.add_argument("--layout", default="csc", choices=["csc", "csr"])
-    ap.add_argument("--path", default="auto", choices=["auto", "scatter", "cart"])
+    ap.add_argument("--path", default="auto", choices=["auto", "scatter", "cart", "gather"])
     ap.add_argument("--kernel", default="auto", choices=["auto", "mma", "gath", "gath1", "sweep"], help="structured-path kernel generation (A/B)")
     ap.add_argument("--xchunk", type=int, default=0, help="quad columns per x-chunk (0: chosen by the library)")
     ap.add_argument("--cpu-mesh", type=int, default=512)
@@ -204,7 +204,7 @@ def main():
     t0 = time.perf_counter()
     if args.mesh_type == "tri":
         if world > 1:
-            raise SystemExit("bench.py: the triangle (scatter) path runs on one GPU")
+            raise SystemExit("bench.py: the triangle path runs on one GPU")
         model = gm.fe.square_tri_model(args.mesh, jitter=0.2, seed=3)
         args.no_cpu = True   # (the CPU baseline leg is defined on the quad workload)
     else:
@@ -215,7 +215,7 @@ def main():
         sp = gm.fe.build_spaces(model, TURAN["V"], TURAN["Ttags"], TURAN["Texpr"])
     x_host = gm.fe.splitmix_iterate(sp.n_total, 1234)
     t_tables = time.perf_counter() - t0
-    pathid = {"auto": capi.GM_PATH_AUTO, "scatter": capi.GM_PATH_SCATTER, "cart": capi.GM_PATH_CART}[args.path]
+    pathid = {"auto": capi.GM_PATH_AUTO, "scatter": capi.GM_PATH_SCATTER, "cart": capi.GM_PATH_CART, "gather": capi.GM_PATH_GATHER}[args.path]
     kid = {"auto": capi.GM_KERNEL_AUTO, "mma": capi.GM_KERNEL_MMA, "gath": capi.GM_KERNEL_GATH, "gath1": capi.GM_KERNEL_GATH1,
            "sweep": capi.GM_KERNEL_SWEEP}[args.kernel]
     h = capi.Handle(sp, layout=args.layout, device=local, path=pathid, rank=rank, nranks=world, kernel=kid, xchunk=args.xchunk)
@@ -438,7 +438,7 @@ def main():
            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
            "data": "synthetic",
            "config": {"workload": workload_name(args), "ncells": sp.model.ncells, "n_free": sp.n_total, "nnz": nnz_global, "nnz_local": nnz,
-                      "layout": args.layout, "path": {1: "scatter", 2: "cart"}[info["active_path"]], "kernel": args.kernel,
+                      "layout": args.layout, "path": {1: "scatter", 2: "cart", 3: "gather"}[info["active_path"]], "kernel": args.kernel,
                       "l2": "outputs (%.1f GB) exceed L2 by >100x; no flush needed" % (8 * nnz / 1e9),
                       "parallelism": ("%d owner-computes row blocks, NCCL send/recv interface-row sum" % world) if world > 1 else "single",
                       "exchange_ms": timing_last.get("exchange_ms"),

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(HERE, "libgemotion_b200.so")
 GM_QUAD, GM_TRI = 0, 1
 GM_LAYOUT_CSC, GM_LAYOUT_CSR = 0, 1
 GM_JACOBIAN, GM_RESIDUAL, GM_CHECK_FINITE, GM_NO_EXCHANGE = 1, 2, 4, 8
-GM_PATH_AUTO, GM_PATH_SCATTER, GM_PATH_CART = 0, 1, 2
+GM_PATH_AUTO, GM_PATH_SCATTER, GM_PATH_CART, GM_PATH_GATHER = 0, 1, 2, 3
 GM_KERNEL_AUTO, GM_KERNEL_MMA, GM_KERNEL_GATH, GM_KERNEL_GATH1, GM_KERNEL_SWEEP = 0, 1, 2, 3, 4
 
 EXPORTS = ["gm_version", "gm_last_error", "gm_create", "gm_destroy", "gm_set_params", "gm_pattern",

@@ -1,0 +1,163 @@
+// gm_gather.cuh -- host side of the generic owner-computes path (kernels: gm_gather_kernel.cuh).
+// GM_PATH_GATHER: the default for every mesh that is not a verified Cartesian strip mesh (Gmsh triangles, kuehn.jl:13-22).
+#pragma once
+#include "gm_internal.h"
+#include "gm_gather_kernel.cuh"
+
+struct gm_gather {
+  GmConst *d_const = nullptr;  // per handle: uploads are ordered on the handle's stream, handles never share it
+  double *cm = nullptr;        // [ncells][NEC] cell matrices (touched blocks, major-major)
+  double *cr = nullptr;        // [ncells][ld]  cell residuals
+  GgDesc *desc = nullptr;      // [ngroup][GG_MPW] records of the velocity / temperature majors, groups sorted by first incident cell
+  int64_t ngroup = 0;
+  int lstride = 96;
+};
+
+// one 64-byte record per velocity / temperature major (list base, length, incident cells) + the longest list;
+// key[group] = first incident cell of the group (its processing order in k_lists)
+__global__ void k_gg_desc(int64_t nU, int64_t oT, int64_t n, int ld, const int64_t *__restrict__ adjptr, const int32_t *__restrict__ adj,
+                          const int64_t *__restrict__ ptr, GgDesc *__restrict__ desc, int32_t *__restrict__ key, int32_t *__restrict__ gid,
+                          int *__restrict__ maxlen) {
+  const int64_t wg = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t nUp = (nU + GG_MPW - 1) / GG_MPW * GG_MPW;
+  if (wg >= (nUp + (n - oT) + GG_MPW - 1) / GG_MPW * GG_MPW) return;
+  GgDesc d;
+  const bool real = wg < nU || (wg >= nUp && wg - nUp + oT < n);
+  const int64_t j = wg < nU ? wg : wg - nUp + oT;
+  d.isU = wg < nUp ? 1 : 0;
+  if (!real) {  // padding: the lists of a group are adjacent in nzval
+    d.p0 = ptr[wg < nUp ? nU : n]; d.j = -1; d.len = 0; d.cnt = 0;
+    for (int t = 0; t < 10; ++t) d.e[t] = 0;
+  } else {
+    const int64_t a0 = adjptr[j];
+    d.p0 = ptr[j];
+    d.j = (int32_t)j;
+    d.len = (int32_t)(ptr[j + 1] - d.p0);
+    d.cnt = (int32_t)(adjptr[j + 1] - a0);
+    for (int t = 0; t < 10; ++t) d.e[t] = t < d.cnt ? adj[a0 + t] : 0;
+    atomicMax(maxlen, d.len);
+  }
+  desc[wg] = d;
+  if (wg % GG_MPW == 0) {
+    key[wg / GG_MPW] = real && d.cnt > 0 ? d.e[0] / ld : 0x7fffffff;
+    gid[wg / GG_MPW] = (int32_t)(wg / GG_MPW);
+  }
+}
+__global__ void k_gg_permute(int64_t ngroup, const int32_t *__restrict__ gid, const GgDesc *__restrict__ src, GgDesc *__restrict__ dst) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // one thread per 16-byte quarter record
+  if (t >= ngroup * GG_MPW * 4) return;
+  const int64_t g = t / (GG_MPW * 4), r = t - g * (GG_MPW * 4);
+  reinterpret_cast<int4 *>(dst)[t] = reinterpret_cast<const int4 *>(src)[(int64_t)gid[g] * (GG_MPW * 4) + r];
+}
+
+static void gm_gather_destroy(gm_handle *h) {
+  gm_gather *g = (gm_gather *)h->gather;
+  if (g) {
+    cudaFree(g->d_const); cudaFree(g->cm); cudaFree(g->cr); cudaFree(g->desc);
+    delete g;
+  }
+  h->gather = nullptr;
+  cudaFree(h->g_adjptr); cudaFree(h->g_adj); cudaFree(h->g_rank); cudaFree(h->g_rankp);
+  h->g_adjptr = nullptr; h->g_adj = nullptr; h->g_rank = nullptr; h->g_rankp = nullptr;
+}
+
+// workspaces, after the symbolic pass
+static int gm_gather_after_pattern(gm_handle *h) {
+  gm_gather *g = new (std::nothrow) gm_gather();
+  if (!g) return GM_ERR_OOM;
+  h->gather = g;
+  const int64_t nec = (int64_t)2 * h->nn * h->ld + 3 * h->nn * h->nn;
+  int rc = gm_dalloc(h, &g->d_const, 1);
+  if (rc == GM_OK) rc = gm_dalloc(h, &g->cm, h->ncells * nec);
+  if (rc == GM_OK) rc = gm_dalloc(h, &g->cr, h->ncells * h->ld);
+  if (rc != GM_OK) {
+    gm_set_error("gm_pattern: the gather path needs %lld bytes of cell-matrix workspace (use GM_PATH_SCATTER for meshes that do not fit)",
+                 (long long)(8 * h->ncells * nec));
+    return rc;
+  }
+  static_assert(sizeof(GgDesc) == 64, "one 64-byte record per major");
+  const int64_t nrec = ((h->off[1] + GG_MPW - 1) / GG_MPW * GG_MPW + (h->n_total - h->off[2]) + GG_MPW - 1) / GG_MPW * GG_MPW;
+  g->ngroup = nrec / GG_MPW;
+  if (g->ngroup == 0) return GM_OK;
+  GgDesc *tmpd = nullptr;
+  int32_t *key = nullptr, *gid = nullptr, *key2 = nullptr, *gid2 = nullptr;
+  int *d_max = nullptr, hmax = 0;
+  void *tmp = nullptr;
+  size_t tb = 0;
+  rc = gm_dalloc(h, &g->desc, nrec);
+  if (rc) return rc;
+  cudaError_t e = cudaMalloc(&tmpd, sizeof(GgDesc) * nrec);
+  if (e == cudaSuccess) e = cudaMalloc(&key, 4 * g->ngroup);
+  if (e == cudaSuccess) e = cudaMalloc(&gid, 4 * g->ngroup);
+  if (e == cudaSuccess) e = cudaMalloc(&key2, 4 * g->ngroup);
+  if (e == cudaSuccess) e = cudaMalloc(&gid2, 4 * g->ngroup);
+  if (e == cudaSuccess) e = cudaMalloc(&d_max, sizeof(int));
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_max, 0, sizeof(int), h->stream);
+  if (e == cudaSuccess) {
+    k_gg_desc<<<gm_blocks(nrec, 256), 256, 0, h->stream>>>(h->off[1], h->off[2], h->n_total, h->ld, h->g_adjptr, h->g_adj, h->ptr, tmpd, key, gid, d_max);
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, key, key2, gid, gid2, (int)g->ngroup, 0, 32, h->stream);
+    e = cudaMalloc(&tmp, tb ? tb : 16);
+  }
+  if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(tmp, tb, key, key2, gid, gid2, (int)g->ngroup, 0, 32, h->stream);  // (stable)
+  if (e == cudaSuccess) {
+    k_gg_permute<<<gm_blocks(nrec * 4, 256), 256, 0, h->stream>>>(g->ngroup, gid2, tmpd, g->desc);
+    e = cudaMemcpyAsync(&hmax, d_max, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(tmpd); cudaFree(key); cudaFree(gid); cudaFree(key2); cudaFree(gid2); cudaFree(d_max); cudaFree(tmp);
+  if (e != cudaSuccess) { gm_set_error("gm_pattern: %s", cudaGetErrorString(e)); return e == cudaErrorMemoryAllocation ? GM_ERR_OOM : GM_ERR_CUDA; }
+  h->max_row_len = hmax;
+  g->lstride = (hmax + 3) & ~3;
+  return GM_OK;
+}
+
+template <int NN, int NQ, int NV, int CPB, bool CSR>
+static int gm_gather_cellmat(gm_handle *h, GgArgs &a) {
+  const size_t sm = sizeof(GgSmem<NN, NQ, NV, CPB>);
+  // (per device, not per process: set on every launch -- a handle on another device of the same process needs it too)
+  GM_CUDA(cudaFuncSetAttribute(k_cellmat<NN, NQ, NV, CPB, CSR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  int per_sm = 0;
+  GM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cellmat<NN, NQ, NV, CPB, CSR>, NN * CPB, sm));
+  if (per_sm < 1) per_sm = 1;
+  const int64_t nbatch = (h->ncells + CPB - 1) / CPB;
+  a.nbatch = (int)nbatch;
+  const int64_t grid = std::min<int64_t>(nbatch, (int64_t)h->num_sms * per_sm);  // persistent: every CTA loops over batches
+  k_cellmat<NN, NQ, NV, CPB, CSR><<<(unsigned)grid, NN * CPB, sm, h->stream>>>(a);
+  return GM_OK;
+}
+
+template <int NN, int NQ, int NV, int CPB>
+static int gm_gather_launch(gm_handle *h, GgArgs &a, int64_t *launches) {
+  const int rc = h->d.layout == GM_LAYOUT_CSR ? gm_gather_cellmat<NN, NQ, NV, CPB, true>(h, a) : gm_gather_cellmat<NN, NQ, NV, CPB, false>(h, a);
+  if (rc) return rc;
+  ++*launches;
+  const int64_t nw = a.ngroup;  // warps
+  if (nw > 0) {
+    const size_t sml = sizeof(double) * GG_LWARPS * GG_MPW * a.lstride;
+    GM_CUDA(cudaFuncSetAttribute(k_lists<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sml));
+    k_lists<NN><<<(unsigned)((nw + GG_LWARPS - 1) / GG_LWARPS), GG_LWARPS * 32, sml, h->stream>>>(a);
+    ++*launches;
+  }
+  GM_CUDA(cudaGetLastError());
+  return GM_OK;
+}
+
+static int gm_gather_run(gm_handle *h, const double *d_x, double *d_nz, double *d_b, unsigned flags, int64_t *launches) {
+  gm_gather *g = (gm_gather *)h->gather;
+  if (!g) { gm_set_error("gm_assemble: gather path without workspaces"); return GM_ERR_STATE; }
+  GmConst &c = h->hc;
+  c.Pr = h->prm.Pr; c.Ra = h->prm.Ra; c.n = h->prm.n; c.reg = h->prm.reg;
+  c.gx = h->prm.gx; c.gy = h->prm.gy; c.jac_scaling = h->prm.jac_scaling;
+  GM_CUDA(cudaMemcpyAsync(g->d_const, &c, sizeof(GmConst), cudaMemcpyHostToDevice, h->stream));  // (pageable source: staged before the call returns)
+  GgArgs a;
+  a.ncells = h->ncells;
+  a.nU = h->off[1]; a.oT = h->off[2]; a.n = h->n_total;
+  a.gc = g->d_const;
+  a.gdofs = h->gdofs; a.dvals = h->dvals; a.coords = h->coords; a.cellv = h->cellv;
+  a.ptr = h->ptr; a.grank = h->g_rank; a.grankp = h->g_rankp; a.adjptr = h->g_adjptr; a.adj = h->g_adj;
+  a.x = d_x; a.cm = g->cm; a.cr = g->cr; a.nz = d_nz; a.b = d_b;
+  a.flags = flags & (GM_JACOBIAN | GM_RESIDUAL);
+  a.desc = g->desc; a.lstride = g->lstride; a.ngroup = g->ngroup;
+  if (h->d.cell_type == GM_QUAD) return gm_gather_launch<9, 4, 4, 16>(h, a, launches);
+  return gm_gather_launch<6, 3, 3, 16>(h, a, launches);
+}

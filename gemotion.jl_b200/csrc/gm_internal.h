@@ -7,26 +7,10 @@
 #include <vector>
 
 #include "../../include/gemotion_b200.h"
-
-#define GM_MAXQ 4
-#define GM_MAXNN 9
-#define GM_MAXNV 4
-#define GM_MAXLD (3 * GM_MAXNN + 3)
+#include "gm_const.h"
 
 struct gm_params {
   double Pr, Ra, n, reg, gx, gy, jac_scaling;
-};
-
-// Reference tables + parameters as seen by the kernels (lives in __constant__ memory).
-struct GmConst {
-  double w[GM_MAXQ];
-  double phi[GM_MAXQ * GM_MAXNN];
-  double dphi[GM_MAXQ * GM_MAXNN * 2];
-  double psi[GM_MAXQ * 3];
-  double dgphi[GM_MAXQ * GM_MAXNV * 2];
-  double Pr, Ra, n, reg, gx, gy, jac_scaling;
-  double hx, hy;
-  int cartesian, nx, ny, layout;
 };
 
 struct gm_handle {
@@ -61,6 +45,11 @@ struct gm_handle {
   void *cart = nullptr;
   void *multi = nullptr;  // gm_multi (row-block interface exchange)
   void *post = nullptr;   // gm_post (post-processing assemblies, gm_post.cuh)
+  // generic owner-computes path (gm_gather.cuh): adjacency dof -> (cell*ld + local) in ascending order, compact cell->nnz map
+  int64_t *g_adjptr = nullptr;
+  int32_t *g_adj = nullptr;
+  uint16_t *g_rank = nullptr, *g_rankp = nullptr;
+  void *gather = nullptr;  // gm_gather: workspaces + device copy of the constants
   // staging for the host API
   double *d_x = nullptr, *d_b = nullptr, *d_nz = nullptr;
   int64_t d_nz_cap = 0;

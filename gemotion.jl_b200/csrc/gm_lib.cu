@@ -12,6 +12,7 @@
 #include "gm_internal.h"
 #include "gm_pattern.cuh"
 #include "gm_scatter.cuh"
+#include "gm_gather.cuh"
 #include "gm_multi.cuh"
 #include "gm_cart.cuh"
 #include "gm_post.cuh"
@@ -116,7 +117,7 @@ extern "C" int gm_create(const gm_desc *d, gm_handle **out) {
       gm_set_error("gm_create: inconsistent Cartesian description");
       return GM_ERR_ARG;
     }
-    if ((d->ghost_lo || d->ghost_hi) && d->path == GM_PATH_SCATTER) {
+    if ((d->ghost_lo || d->ghost_hi) && (d->path == GM_PATH_SCATTER || d->path == GM_PATH_GATHER)) {
       gm_set_error("gm_create: row blocks with ghost rows need the structured path");
       return GM_ERR_ARG;
     }
@@ -212,15 +213,17 @@ extern "C" int gm_create(const gm_desc *d, gm_handle **out) {
       for (size_t k = 0; k < cv.size(); ++k) cv[k] = d->cell_vertices[k] - d->vertex_index_base;
       TRY(gm_upload(h, &h->cellv, cv.data(), (int64_t)cv.size()));
     }
-    TRY(gm_color_generic(h, d));
+    if (d->path == GM_PATH_SCATTER) TRY(gm_color_generic(h, d));
   } else {
     h->ncolors = 4;
   }
   TRY(gm_dalloc(h, &h->d_x, h->n_total));
   TRY(gm_dalloc(h, &h->d_b, h->n_total));
-  h->active_path = GM_PATH_SCATTER;
-  if (d->cartesian && d->path != GM_PATH_SCATTER) {
-    rc = gm_cart_create(h);  // verifies the tables; keeps the scatter path if they do not fit
+  // generic meshes: owner-computes gather unless the caller asks for the colour-ordered scatter
+  h->active_path = d->path == GM_PATH_SCATTER ? GM_PATH_SCATTER : GM_PATH_GATHER;
+  if (d->path < GM_PATH_AUTO || d->path > GM_PATH_GATHER) { gm_set_error("gm_create: bad path"); return fail(GM_ERR_ARG); }
+  if (d->cartesian && (d->path == GM_PATH_AUTO || d->path == GM_PATH_CART)) {
+    rc = gm_cart_create(h);  // verifies the tables; falls back to the generic gather if they do not fit
     if (rc != GM_OK && d->path == GM_PATH_CART) return fail(rc);
   } else if (d->path == GM_PATH_CART) {
     gm_set_error("gm_create: GM_PATH_CART needs a Cartesian description");
@@ -242,6 +245,7 @@ extern "C" void gm_destroy(gm_handle *h) {
   gm_multi_destroy(h);
   gm_post_destroy(h);
   gm_cart_destroy(h);
+  gm_gather_destroy(h);
   cudaFree(h->gdofs); cudaFree(h->dvals); cudaFree(h->coords); cudaFree(h->cellv);
   cudaFree(h->ptr); cudaFree(h->idx); cudaFree(h->rank); cudaFree(h->color_cells);
   cudaFree(h->d_x); cudaFree(h->d_b); cudaFree(h->d_nz);
@@ -275,6 +279,10 @@ extern "C" int gm_pattern(gm_handle *h, int64_t *nnz) {
     if (rc) return rc;
     if (h->active_path == GM_PATH_CART) {
       rc = gm_cart_after_pattern(h);
+      if (rc) return rc;
+    }
+    if (h->active_path == GM_PATH_GATHER) {
+      rc = gm_gather_after_pattern(h);
       if (rc) return rc;
     }
     if (h->d.ghost_lo || h->d.ghost_hi) {
@@ -437,6 +445,7 @@ static int gm_run(gm_handle *h, const double *d_x, double *d_nz, double *d_b, ui
   if ((flags & GM_RESIDUAL) && !d_b) { gm_set_error("gm_assemble: GM_RESIDUAL without resid"); return GM_ERR_ARG; }
   if (!(flags & (GM_JACOBIAN | GM_RESIDUAL))) { gm_set_error("gm_assemble: nothing to do"); return GM_ERR_ARG; }
   if (h->active_path == GM_PATH_CART) return gm_cart_run(h, d_x, d_nz, d_b, flags, launches);  // (parameters travel as kernel arguments)
+  if (h->active_path == GM_PATH_GATHER) return gm_gather_run(h, d_x, d_nz, d_b, flags, launches);
   int rc = gm_upload_const(h);
   if (rc) return rc;
   rc = gm_launch_scatter(h, d_x, d_nz, d_b, flags, launches);

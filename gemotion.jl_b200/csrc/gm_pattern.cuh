@@ -59,11 +59,25 @@ __global__ void k_fill_adj(int64_t nent, const int32_t *__restrict__ g, const in
   }
 }
 
+// ascending (cell, local) order inside every dof's adjacency segment: the gather path sums a list's contributions in
+// Gridap's cell-loop order, independent of the atomics of k_fill_adj
+__global__ void k_sort_adj(int64_t n, const int64_t *__restrict__ adjptr, int32_t *__restrict__ adj) {
+  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int64_t a0 = adjptr[r], a1 = adjptr[r + 1];
+  for (int64_t i = a0 + 1; i < a1; ++i) {
+    const int32_t v = adj[i];
+    int64_t k = i;
+    while (k > a0 && adj[k - 1] > v) { adj[k] = adj[k - 1]; --k; }
+    adj[k] = v;
+  }
+}
+
 // Thread per major dof.  PASS 0: row length.  PASS 1: write idx and the rank table.
 template <int PASS>
 __global__ void k_rows(int64_t n, int nn, const int32_t *__restrict__ g, const int64_t *__restrict__ adjptr,
                        const int32_t *__restrict__ adj, int64_t *__restrict__ len_or_ptr, int32_t *__restrict__ idx,
-                       uint16_t *__restrict__ rank, int *__restrict__ err) {
+                       uint16_t *__restrict__ rank, uint16_t *__restrict__ grank, uint16_t *__restrict__ grankp, int *__restrict__ err) {
   const int ld = 3 * nn + 3;
   int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= n) return;
@@ -114,7 +128,14 @@ __global__ void k_rows(int64_t n, int nn, const int32_t *__restrict__ g, const i
         }
         rk = (uint16_t)lo;
       }
-      rank[(c * ld + l) * ld + M] = rk;
+      if (rank) rank[(c * ld + l) * ld + M] = rk;
+      if (grank && gm_touched(fM, gm_field_of(l, nn))) {
+        // compact major-major layout of the gather path (gm_gather_kernel.cuh): [U majors][T majors]; P majors apart
+        const int offT = 2 * nn * ld, nec = offT + nn * 3 * nn;
+        const int s = (fM == 2 && l >= 2 * nn) ? l - 3 : l;
+        if (fM == 1) grankp[c * 6 * nn + (M - 2 * nn) * 2 * nn + s] = rk;
+        else grank[c * nec + (fM == 0 ? M * ld : offT + (M - 2 * nn - 3) * 3 * nn) + s] = rk;
+      }
     }
   }
 }
@@ -131,6 +152,7 @@ static int gm_build_pattern(gm_handle *h) {
   const int BS = 256;
   int32_t *cnt = nullptr, *adj = nullptr;
   int64_t *adjptr = nullptr, *len = nullptr;
+  uint16_t *grank = nullptr, *grankp = nullptr;
   int *err = nullptr;
   void *tmp = nullptr;
   size_t tmpb = 0;
@@ -156,8 +178,9 @@ static int gm_build_pattern(gm_handle *h) {
   BAILC(cub::DeviceScan::ExclusiveSum(tmp, tmpb, cnt, adjptr, n + 1, h->stream));
   BAILC(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * (n + 1), h->stream));
   k_fill_adj<<<gm_blocks(nent, BS), BS, 0, h->stream>>>(nent, h->gdofs, adjptr, cnt, adj);
+  k_sort_adj<<<gm_blocks(n, BS), BS, 0, h->stream>>>(n, adjptr, adj);
   BAILC(cudaMemsetAsync(len, 0, sizeof(int64_t) * (n + 1), h->stream));
-  k_rows<0><<<gm_blocks(n, 128), 128, 0, h->stream>>>(n, h->nn, h->gdofs, adjptr, adj, len, nullptr, nullptr, err);
+  k_rows<0><<<gm_blocks(n, 128), 128, 0, h->stream>>>(n, h->nn, h->gdofs, adjptr, adj, len, nullptr, nullptr, nullptr, nullptr, err);
   {
     // max row length (for diagnostics / uint16 safety) and prefix sum
     BAIL(gm_dalloc(h, &h->ptr, n + 1));
@@ -175,18 +198,33 @@ static int gm_build_pattern(gm_handle *h) {
   }
   BAIL(gm_dalloc(h, &h->idx, h->nnz));
   keep += (int64_t)sizeof(int32_t) * (h->nnz > 0 ? h->nnz : 1);
-  BAIL(gm_dalloc(h, &h->rank, h->ncells * h->ld * h->ld));
-  keep += (int64_t)sizeof(uint16_t) * h->ncells * h->ld * h->ld;
-  k_fill_u16<<<gm_blocks(h->ncells * h->ld * h->ld, BS), BS, 0, h->stream>>>(h->rank, h->ncells * h->ld * h->ld, 0xFFFF);
-  k_rows<1><<<gm_blocks(n, 128), 128, 0, h->stream>>>(n, h->nn, h->gdofs, adjptr, adj, h->ptr, h->idx, h->rank, err);
+  if (h->active_path == GM_PATH_GATHER) {  // compact map of the gather path; the adjacency is kept (gm_gather.cuh)
+    const int64_t nec = (int64_t)2 * h->nn * h->ld + 3 * h->nn * h->nn, nep = 6 * h->nn;
+    BAIL(gm_dalloc(h, &grank, h->ncells * nec));
+    BAIL(gm_dalloc(h, &grankp, h->ncells * nep));
+    keep += (int64_t)sizeof(uint16_t) * h->ncells * (nec + nep) + (int64_t)sizeof(int32_t) * nent + (int64_t)sizeof(int64_t) * (n + 1);
+    k_fill_u16<<<gm_blocks(h->ncells * nec, BS), BS, 0, h->stream>>>(grank, h->ncells * nec, 0xFFFF);
+    k_fill_u16<<<gm_blocks(h->ncells * nep, BS), BS, 0, h->stream>>>(grankp, h->ncells * nep, 0xFFFF);
+  } else {
+    BAIL(gm_dalloc(h, &h->rank, h->ncells * h->ld * h->ld));
+    keep += (int64_t)sizeof(uint16_t) * h->ncells * h->ld * h->ld;
+    k_fill_u16<<<gm_blocks(h->ncells * h->ld * h->ld, BS), BS, 0, h->stream>>>(h->rank, h->ncells * h->ld * h->ld, 0xFFFF);
+  }
+  k_rows<1><<<gm_blocks(n, 128), 128, 0, h->stream>>>(n, h->nn, h->gdofs, adjptr, adj, h->ptr, h->idx, h->rank, grank, grankp, err);
   BAILC(cudaGetLastError());
   BAILC(cudaStreamSynchronize(h->stream));
   h->has_pattern = true;
+  if (h->active_path == GM_PATH_GATHER) {
+    h->g_adjptr = adjptr; h->g_adj = adj; h->g_rank = grank; h->g_rankp = grankp;
+    adjptr = nullptr; adj = nullptr; grank = nullptr; grankp = nullptr;
+  }
 done:
   cudaFree(tmp);
   cudaFree(cnt);
   cudaFree(adjptr);
   cudaFree(adj);
+  cudaFree(grank);
+  cudaFree(grankp);
   cudaFree(len);
   cudaFree(err);
   h->device_bytes = keep;

@@ -63,9 +63,10 @@ enum gm_layout { GM_LAYOUT_CSC = 0, GM_LAYOUT_CSR = 1 };
 
 /* Numeric kernels */
 enum gm_path {
-  GM_PATH_AUTO = 0,    /* structured if the tables verify as a Cartesian strip mesh, else scatter */
-  GM_PATH_SCATTER = 1, /* colour-ordered atomic-free scatter, any mesh */
-  GM_PATH_CART = 2     /* structured owner-computes row gather, Cartesian quads only */
+  GM_PATH_AUTO = 0,    /* structured if the tables verify as a Cartesian strip mesh, else gather */
+  GM_PATH_SCATTER = 1, /* colour-ordered atomic-free scatter, any mesh (first generation, kept for A/B) */
+  GM_PATH_CART = 2,    /* structured owner-computes row gather, Cartesian quads only */
+  GM_PATH_GATHER = 3   /* cell matrices by node pairs + owner-computes list gather, any mesh (Gmsh triangles) */
 };
 
 /* Kernel generation of the structured path (A/B measurements, parity tests of the older generations) */

@@ -59,3 +59,27 @@ def nz_blocks(sp, ptr, idx):
 def res_blocks(sp):
     f = field_of_dof(sp)
     return [f == a for a in range(3)]
+
+
+def fan_model(valence=14):
+    """A vertex of high valence: `valence` triangles around the centre (lists longer than 96 entries, more incident cells than a
+    major's 64-byte record holds inline), one ring of 2*valence triangles around them; the outer boundary is tagged "wall"."""
+    k = valence
+    ang = 2 * np.pi * np.arange(k) / k
+    ring1 = np.stack([np.cos(ang), np.sin(ang)], axis=1) * (1.0 + 0.1 * np.cos(3 * ang))[:, None]
+    ring2 = np.stack([np.cos(ang + np.pi / k), np.sin(ang + np.pi / k)], axis=1) * 2.0
+    coords = np.concatenate([[[0.05, -0.03]], ring1, ring2])
+    tris, bnd = [], {}
+    for i in range(k):
+        a, b = 1 + i, 1 + (i + 1) % k
+        c, cprev = 1 + k + i, 1 + k + (i - 1) % k
+        tris.append((0, a, b))       # fan
+        tris.append((a, b, c))       # ring1 edge -> outer vertex between them
+        tris.append((a, cprev, c))   # outer edge (cprev, c) -> ring1 vertex a
+        bnd[(min(cprev, c), max(cprev, c))] = 1
+    vent = np.zeros(coords.shape[0], dtype=np.int32)
+    vent[1 + k:] = 1
+    return fe.TriangleModel(coords, tris, vent, bnd, {"wall": [1], "all": [1]})
+
+
+FAN = dict(V=["wall"], Ttags=["wall"], Texpr=[lambda x: 0.5 + 0.25 * x[0]])

@@ -28,6 +28,7 @@ def _models():
     yield "cart2x3_wave", cases.cart(2, 3, bc=cases.WAVE)
     yield "annulus", cases.spaces(fe.annulus_model(nr=4, nt=16, jitter=0.3, seed=1), cases.KUEHN)
     yield "sqtri", cases.spaces(fe.square_tri_model(6, jitter=0.3, seed=2), cases.TURAN)
+    yield "fan14", cases.spaces(cases.fan_model(14), cases.FAN)
 
 
 MODELS = dict(_models())
@@ -78,6 +79,29 @@ def test_scatter_path_matches_oracle(gm, gpu_lib, name, pi, layout):
     assert info["active_path"] == gm.capi.GM_PATH_SCATTER
 
 
+@pytest.mark.parametrize("name", list(MODELS))
+@pytest.mark.parametrize("pi", range(len(PARAMS)))
+@pytest.mark.parametrize("layout", ["csc", "csr"])
+def test_gather_path_matches_oracle(gm, gpu_lib, name, pi, layout):
+    """Generic owner-computes path (gm_gather.cuh: cell matrices by node pairs + list gather): triangles and quads."""
+    sp = MODELS[name]
+    x = fe.splitmix_iterate(sp.n_total, 1234)
+    info = _check(gm, sp, PARAMS[pi], layout, gm.capi.GM_PATH_GATHER, x)
+    assert info["active_path"] == gm.capi.GM_PATH_GATHER
+
+
+def test_gather_path_on_a_gmsh_file(gm, gpu_lib, tmp_path):
+    """A triangle mesh read back from a .msh file (format 4.1, physical names -> tags) through the default path."""
+    from _pkg import gm as pkg
+    model = fe.annulus_model(nr=6, nt=40, jitter=0.3, seed=11)
+    path = str(tmp_path / "annulus.msh")
+    pkg.gmsh.write_msh(model, path, version="4.1")
+    sp = cases.spaces(pkg.gmsh.read_msh(path), cases.KUEHN)
+    x = fe.splitmix_iterate(sp.n_total, 99)
+    info = _check(gm, sp, dict(Pr=0.706, Ra=4.7e4, n=0.8), "csc", gm.capi.GM_PATH_AUTO, x)
+    assert info["active_path"] == gm.capi.GM_PATH_GATHER
+
+
 def test_smooth_iterate_and_zero(gm, gpu_lib):
     sp = cases.cart(16, bc=cases.TURAN)
     for x in (fe.smooth_iterate(sp), np.zeros(sp.n_total)):
@@ -103,14 +127,14 @@ def test_error_paths(gm, gpu_lib):
     h.close()
 
 
-@pytest.mark.parametrize("path", ["scatter", "cart"])
+@pytest.mark.parametrize("path", ["scatter", "cart", "gather"])
 def test_check_finite_flag_scans_on_the_device(gm, gpu_lib, path):
     """GM_CHECK_FINITE: a NaN in the iterate must surface as GM_ERR_NONFINITE (-6) from both entry points, for nzval and for
     the residual; a clean iterate passes."""
     import torch
     capi = gm.capi
     sp = cases.cart(9, 6, bc=cases.TURAN)
-    h = capi.Handle(sp, path=capi.GM_PATH_SCATTER if path == "scatter" else capi.GM_PATH_CART)
+    h = capi.Handle(sp, path={"scatter": capi.GM_PATH_SCATTER, "cart": capi.GM_PATH_CART, "gather": capi.GM_PATH_GATHER}[path])
     try:
         h.set_params(Pr=100.0, Ra=1e5, n=0.6)
         nnz = h.pattern()
@@ -140,7 +164,8 @@ def test_two_handles_one_process_interleaved(gm, gpu_lib):
     spa, spb = cases.cart(24, 16, bc=cases.TURAN), cases.spaces(fe.square_tri_model(10, jitter=0.2, seed=4), cases.TURAN)
     pa, pb = dict(Pr=100.0, Ra=1e5, n=0.6), dict(Pr=0.7, Ra=1e3, n=1.0)
     items = []
-    for sp, prm, path in ((spa, pa, capi.GM_PATH_SCATTER), (spb, pb, capi.GM_PATH_SCATTER), (spa, pb, capi.GM_PATH_CART)):
+    for sp, prm, path in ((spa, pa, capi.GM_PATH_SCATTER), (spb, pb, capi.GM_PATH_SCATTER), (spa, pb, capi.GM_PATH_CART),
+                          (spb, pa, capi.GM_PATH_GATHER), (spa, pb, capi.GM_PATH_GATHER)):
         h = capi.Handle(sp, path=path)
         h.set_params(**prm)
         nnz = h.pattern()
@@ -395,4 +420,6 @@ def test_config3_annulus_kuehn_size(gm, gpu_lib):
     assert sp.model.ncells == 2 * 18 * 128
     x = fe.splitmix_iterate(sp.n_total, 1234)
     info = _check(gm, sp, dict(Pr=0.706, Ra=4.7e4, n=1.0), "csc", gm.capi.GM_PATH_AUTO, x)
+    assert info["active_path"] == gm.capi.GM_PATH_GATHER
+    info = _check(gm, sp, dict(Pr=0.706, Ra=4.7e4, n=1.0), "csc", gm.capi.GM_PATH_SCATTER, x)
     assert info["active_path"] == gm.capi.GM_PATH_SCATTER and info["ncolors"] >= 6
