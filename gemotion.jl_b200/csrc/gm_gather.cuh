@@ -4,6 +4,8 @@
 #include "gm_internal.h"
 #include "gm_gather_kernel.cuh"
 
+#define GG_WINDOW 4096  // cells per locality window of the group order
+
 struct gm_gather {
   GmConst *d_const = nullptr;  // per handle: uploads are ordered on the handle's stream, handles never share it
   double *cm = nullptr;        // [ncells][NEC] cell matrices (touched blocks, major-major)
@@ -39,7 +41,9 @@ __global__ void k_gg_desc(int64_t nU, int64_t oT, int64_t n, int ld, const int64
   }
   desc[wg] = d;
   if (wg % GG_MPW == 0) {
-    key[wg / GG_MPW] = real && d.cnt > 0 ? d.e[0] / ld : 0x7fffffff;
+    // windows of GG_WINDOW cells keep the reads of `cm` local; inside a window the long groups (vertex dofs) come first,
+    // so that the warps of a CTA finish together (a CTA's registers and shared memory are held until its slowest warp ends)
+    key[wg / GG_MPW] = real && d.cnt > 0 ? ((d.e[0] / ld) / GG_WINDOW) * 4 + (wg < nUp ? 0 : 2) + (d.cnt >= 4 ? 0 : 1) : 0x7fffffff;
     gid[wg / GG_MPW] = (int32_t)(wg / GG_MPW);
   }
 }

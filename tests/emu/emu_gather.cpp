@@ -53,7 +53,7 @@ static int run(GgArgs a, bool csr, int grid) {
       for (int t = 0; t < 10; ++t) d.e[t] = t < d.cnt ? a.adj[a0 + t] : 0;
       maxlen = std::max(maxlen, (int)d.len);
     }
-    if (wg % GG_MPW == 0) order[wg / GG_MPW] = {real && d.cnt > 0 ? d.e[0] / ld : 0x7fffffff, (int32_t)(wg / GG_MPW)};
+    if (wg % GG_MPW == 0) order[wg / GG_MPW] = {real && d.cnt > 0 ? ((d.e[0] / ld) / 8) * 4 + (wg < nUp ? 0 : 2) + (d.cnt >= 4 ? 0 : 1) : 0x7fffffff, (int32_t)(wg / GG_MPW)};  // (windows of 8 cells here)
   }
   std::stable_sort(order.begin(), order.end(), [](auto &x, auto &y) { return x.first < y.first; });
   for (int64_t g = 0; g < ngroup; ++g)
