@@ -203,13 +203,14 @@ def main():
     # interface rows summed with NCCL send/recv inside gm_assemble_device.
     t0 = time.perf_counter()
     if args.mesh_type == "tri":
-        if world > 1:
-            raise SystemExit("bench.py: the triangle path runs on one GPU")
         model = gm.fe.square_tri_model(args.mesh, jitter=0.2, seed=3)
         args.no_cpu = True   # (the CPU baseline leg is defined on the quad workload)
     else:
         model = gm.fe.CartesianModel((0, 1, 0, 1), (args.mesh, args.mesh))
-    if world > 1:
+    if world > 1 and args.mesh_type == "tri":
+        # contiguous cell ranges + ghost cells (gather path): no exchange step on the data path
+        sp = gm.fe.build_rank_spaces_cells(model, TURAN["V"], TURAN["Ttags"], TURAN["Texpr"], rank, world)
+    elif world > 1:
         sp = gm.fe.build_rank_spaces(model, TURAN["V"], TURAN["Ttags"], TURAN["Texpr"], rank, world)
     else:
         sp = gm.fe.build_spaces(model, TURAN["V"], TURAN["Ttags"], TURAN["Texpr"])
@@ -224,7 +225,7 @@ def main():
     nnz = h.pattern()
     t_pattern = time.perf_counter() - t0
     info = h.info()
-    if world > 1:
+    if world > 1 and args.mesh_type != "tri":
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             idt = torch.frombuffer(bytearray(capi.nccl_unique_id()), dtype=torch.uint8).cuda()
@@ -440,7 +441,8 @@ def main():
            "config": {"workload": workload_name(args), "ncells": sp.model.ncells, "n_free": sp.n_total, "nnz": nnz_global, "nnz_local": nnz,
                       "layout": args.layout, "path": {1: "scatter", 2: "cart", 3: "gather"}[info["active_path"]], "kernel": args.kernel,
                       "l2": "outputs (%.1f GB) exceed L2 by >100x; no flush needed" % (8 * nnz / 1e9),
-                      "parallelism": ("%d owner-computes row blocks, NCCL send/recv interface-row sum" % world) if world > 1 else "single",
+                      "parallelism": (("%d contiguous cell ranges + ghost cells, no exchange step" % world) if args.mesh_type == "tri" else
+                                      ("%d owner-computes row blocks, NCCL send/recv interface-row sum" % world)) if world > 1 else "single",
                       "exchange_ms": timing_last.get("exchange_ms"),
                       "pattern_s": t_pattern, "tables_s": t_tables, "device_bytes": info["device_bytes"]},
            "roofline": roof, "verify": verify, "parts": parts, "cpu_baseline": cpu, "e2e": e2e, "e2e_note": e2e_note, "gpu_launches": int(launches_per_step * args.steps),

@@ -52,6 +52,7 @@ class gm_desc(C.Structure):
         ("cell_begin", C.c_int64), ("ncells_global", C.c_int64),
         ("ghost_lo", C.c_int32), ("ghost_hi", C.c_int32),
         ("kernel", C.c_int32), ("xchunk", C.c_int32),
+        ("n_own_cells", C.c_int64), ("ghost_cell_ids", C.c_void_p),
     ]
 
 
@@ -151,7 +152,15 @@ class Handle:
             d.h[0], d.h[1] = m.h
         else:
             keep["coords"] = c(m.vertex_coords, dtype=np.float64)
-            keep["cv"] = c(m.cell_vertices, dtype=np.int32)
+            part = getattr(sp, "part", None)   # (c0, c1, ghost cell ids): one rank of a contiguous-cell-range partition
+            keep["cv"] = c(m.cell_vertices if sp.cells is None else m.cell_vertices[sp.cells], dtype=np.int32)
+            if part is not None:
+                c0, c1, ghosts = part
+                keep["ghosts"] = c(ghosts, dtype=np.int64)
+                d.ncells = int(c1 - c0 + len(ghosts))
+                d.n_own_cells = int(c1 - c0)
+                d.cell_begin = int(c0)
+                d.ghost_cell_ids = _p(keep["ghosts"]) if len(ghosts) else None
             d.coords, d.cell_vertices = _p(keep["coords"]), _p(keep["cv"])
         d.vertex_index_base = 0
         d.layout = GM_LAYOUT_CSR if layout == "csr" else GM_LAYOUT_CSC
@@ -171,7 +180,7 @@ class Handle:
         d.device, d.path = device, path
         d.kernel, d.xchunk = kernel, xchunk
         d.rank, d.nranks, d.ncells_global = rank, nranks, m.ncells
-        if rows is None:
+        if rows is None and getattr(sp, "part", None) is None:
             d.cell_begin = 0
         self._h = C.c_void_p()
         self.layout = layout

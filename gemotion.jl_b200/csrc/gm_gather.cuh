@@ -17,9 +17,12 @@ struct gm_gather {
 
 // one 64-byte record per velocity / temperature major (list base, length, incident cells) + the longest list;
 // key[group] = first incident cell of the group (its processing order in k_lists)
+// Partitioned meshes: a major is assembled by this rank iff its lowest-numbered incident cell (GLOBAL id) is an own cell; the
+// others get cnt = 0 (their lists are zero-filled, never summed) and are counted out of n_owned.
 __global__ void k_gg_desc(int64_t nU, int64_t oT, int64_t n, int ld, const int64_t *__restrict__ adjptr, const int32_t *__restrict__ adj,
-                          const int64_t *__restrict__ ptr, GgDesc *__restrict__ desc, int32_t *__restrict__ key, int32_t *__restrict__ gid,
-                          int *__restrict__ maxlen) {
+                          const int64_t *__restrict__ ptr, int64_t nown, int64_t cell_begin, const int64_t *__restrict__ ghost_ids,
+                          GgDesc *__restrict__ desc, int32_t *__restrict__ key, int32_t *__restrict__ gid,
+                          int *__restrict__ maxlen, unsigned long long *__restrict__ nowned) {
   const int64_t wg = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t nUp = (nU + GG_MPW - 1) / GG_MPW * GG_MPW;
   if (wg >= (nUp + (n - oT) + GG_MPW - 1) / GG_MPW * GG_MPW) return;
@@ -36,14 +39,31 @@ __global__ void k_gg_desc(int64_t nU, int64_t oT, int64_t n, int ld, const int64
     d.j = (int32_t)j;
     d.len = (int32_t)(ptr[j + 1] - d.p0);
     d.cnt = (int32_t)(adjptr[j + 1] - a0);
-    for (int t = 0; t < 10; ++t) d.e[t] = t < d.cnt ? adj[a0 + t] : 0;
+    if (ghost_ids) {
+      int64_t lowest = INT64_MAX;
+      for (int t = 0; t < d.cnt; ++t) {
+        const int64_t lc = adj[a0 + t] / ld, gc = lc < nown ? cell_begin + lc : ghost_ids[lc - nown];
+        lowest = gc < lowest ? gc : lowest;
+      }
+      if (!(lowest >= cell_begin && lowest < cell_begin + nown)) { d.cnt = 0; d.j = -1; }
+    }
+    if (d.j >= 0) atomicAdd(nowned, 1ull);
+    for (int t = 0; t < 10; ++t) {
+      uint32_t sg = 0;
+      if (t < d.cnt) {
+        const int32_t e = adj[a0 + t], cc = e / ld;
+        const int M = e - cc * ld, nn = (ld - 3) / 3;
+        sg = (uint32_t)cc * (uint32_t)(2 * nn * ld + 3 * nn * nn) + (M < 2 * nn ? M * ld : 2 * nn * ld + (M - 2 * nn - 3) * 3 * nn);
+      }
+      d.e[t] = sg;
+    }
     atomicMax(maxlen, d.len);
   }
   desc[wg] = d;
   if (wg % GG_MPW == 0) {
     // windows of GG_WINDOW cells keep the reads of `cm` local; inside a window the long groups (vertex dofs) come first,
     // so that the warps of a CTA finish together (a CTA's registers and shared memory are held until its slowest warp ends)
-    key[wg / GG_MPW] = real && d.cnt > 0 ? ((d.e[0] / ld) / GG_WINDOW) * 4 + (wg < nUp ? 0 : 2) + (d.cnt >= 4 ? 0 : 1) : 0x7fffffff;
+    key[wg / GG_MPW] = real && d.cnt > 0 ? ((adj[adjptr[j]] / ld) / GG_WINDOW) * 4 + (wg < nUp ? 0 : 2) + (d.cnt >= 4 ? 0 : 1) : 0x7fffffff;
     gid[wg / GG_MPW] = (int32_t)(wg / GG_MPW);
   }
 }
@@ -71,6 +91,10 @@ static int gm_gather_after_pattern(gm_handle *h) {
   if (!g) return GM_ERR_OOM;
   h->gather = g;
   const int64_t nec = (int64_t)2 * h->nn * h->ld + 3 * h->nn * h->nn;
+  if (h->ncells * nec >= ((int64_t)1 << 32)) {
+    gm_set_error("gm_pattern: the gather path indexes its cell-matrix workspace with 32 bits (%lld cells x %lld values do not fit)", (long long)h->ncells, (long long)nec);
+    return GM_ERR_ARG;
+  }
   int rc = gm_dalloc(h, &g->d_const, 1);
   if (rc == GM_OK) rc = gm_dalloc(h, &g->cm, h->ncells * nec);
   if (rc == GM_OK) rc = gm_dalloc(h, &g->cr, h->ncells * h->ld);
@@ -86,6 +110,7 @@ static int gm_gather_after_pattern(gm_handle *h) {
   GgDesc *tmpd = nullptr;
   int32_t *key = nullptr, *gid = nullptr, *key2 = nullptr, *gid2 = nullptr;
   int *d_max = nullptr, hmax = 0;
+  unsigned long long *d_own = nullptr, hown = 0;
   void *tmp = nullptr;
   size_t tb = 0;
   rc = gm_dalloc(h, &g->desc, nrec);
@@ -97,8 +122,11 @@ static int gm_gather_after_pattern(gm_handle *h) {
   if (e == cudaSuccess) e = cudaMalloc(&gid2, 4 * g->ngroup);
   if (e == cudaSuccess) e = cudaMalloc(&d_max, sizeof(int));
   if (e == cudaSuccess) e = cudaMemsetAsync(d_max, 0, sizeof(int), h->stream);
+  if (e == cudaSuccess) e = cudaMalloc(&d_own, 8);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_own, 0, 8, h->stream);
   if (e == cudaSuccess) {
-    k_gg_desc<<<gm_blocks(nrec, 256), 256, 0, h->stream>>>(h->off[1], h->off[2], h->n_total, h->ld, h->g_adjptr, h->g_adj, h->ptr, tmpd, key, gid, d_max);
+    k_gg_desc<<<gm_blocks(nrec, 256), 256, 0, h->stream>>>(h->off[1], h->off[2], h->n_total, h->ld, h->g_adjptr, h->g_adj, h->ptr, h->n_own_cells,
+                                                          h->d.cell_begin, h->ghost_ids, tmpd, key, gid, d_max, d_own);
     cub::DeviceRadixSort::SortPairs(nullptr, tb, key, key2, gid, gid2, (int)g->ngroup, 0, 32, h->stream);
     e = cudaMalloc(&tmp, tb ? tb : 16);
   }
@@ -106,11 +134,17 @@ static int gm_gather_after_pattern(gm_handle *h) {
   if (e == cudaSuccess) {
     k_gg_permute<<<gm_blocks(nrec * 4, 256), 256, 0, h->stream>>>(g->ngroup, gid2, tmpd, g->desc);
     e = cudaMemcpyAsync(&hmax, d_max, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&hown, d_own, 8, cudaMemcpyDeviceToHost, h->stream);
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-  cudaFree(tmpd); cudaFree(key); cudaFree(gid); cudaFree(key2); cudaFree(gid2); cudaFree(d_max); cudaFree(tmp);
+  cudaFree(tmpd); cudaFree(key); cudaFree(gid); cudaFree(key2); cudaFree(gid2); cudaFree(d_max); cudaFree(d_own); cudaFree(tmp);
   if (e != cudaSuccess) { gm_set_error("gm_pattern: %s", cudaGetErrorString(e)); return e == cudaErrorMemoryAllocation ? GM_ERR_OOM : GM_ERR_CUDA; }
   h->max_row_len = hmax;
+  if (h->ghost_ids) {  // owned dofs of a partitioned mesh: velocity / temperature majors counted above + the pressure dofs of the own cells
+    int64_t np_own = 3 * h->n_own_cells;
+    if (h->d.cell_begin + h->n_own_cells == h->d.ncells_global) np_own -= 1;  // (the fixed last pressure dof, Solver.jl:90)
+    h->n_owned = (int64_t)hown + np_own;
+  }
   g->lstride = (hmax + 3) & ~3;
   return GM_OK;
 }
@@ -155,6 +189,7 @@ static int gm_gather_run(gm_handle *h, const double *d_x, double *d_nz, double *
   GM_CUDA(cudaMemcpyAsync(g->d_const, &c, sizeof(GmConst), cudaMemcpyHostToDevice, h->stream));  // (pageable source: staged before the call returns)
   GgArgs a;
   a.ncells = h->ncells;
+  a.nown = h->n_own_cells;
   a.nU = h->off[1]; a.oT = h->off[2]; a.n = h->n_total;
   a.gc = g->d_const;
   a.gdofs = h->gdofs; a.dvals = h->dvals; a.coords = h->coords; a.cellv = h->cellv;

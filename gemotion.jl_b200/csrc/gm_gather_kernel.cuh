@@ -17,7 +17,8 @@
 //               list is stored once.  The residual entry is the same ordered sum over the cell residuals `cr`.
 //
 // Layout of a cell's NEC = 2NN*LD + 3NN*NN intermediate values (cm) and map entries (grank):
-//   [U majors: 2NN x LD minors][T majors: NN x (2NN velocity + NN temperature minors)];
+//   [U majors: 2NN x LD minors][T majors: NN x (2NN velocity + NN temperature minors)]; cell residuals: cr[cell][LD]
+//   (a compact array of their own: a residual-only call must not leave partially written 32-byte sectors all over cm);
 // the map of the pressure majors (3 x 2NN velocity minors per cell) is a separate array (grankp).
 // "major" = CSC column (trial dof) or CSR row (test dof) by the template flag.
 //
@@ -37,6 +38,7 @@
 
 struct GgArgs {
   int64_t ncells;
+  int64_t nown;       // own cells (the first nown of the tables); the others are ghosts: no pressure rows from them
   int64_t nU, oT, n;  // free velocity dofs, first temperature dof, all free dofs
   const GmConst *gc;  // reference tables + parameters (device copy owned by the handle)
   const int32_t *gdofs;
@@ -101,8 +103,9 @@ struct GgSmem {
 template <int NN>
 struct GgLayout {
   static constexpr int LD = 3 * NN + 3;
-  static constexpr int OFF_T = 2 * NN * LD;
-  static constexpr int NEC = OFF_T + NN * 3 * NN;  // intermediate values / map entries per cell (360 / 783)
+  static constexpr int SU = LD, ST = 3 * NN;  // segment lengths of a velocity / temperature major
+  static constexpr int OFF_T = 2 * NN * SU;
+  static constexpr int NEC = OFF_T + NN * ST;  // intermediate values / map entries per cell (360 / 783)
 };
 
 #ifdef GM_EMU
@@ -127,14 +130,21 @@ __device__ __forceinline__ int32_t gg_lane_word(int32_t v, int src) { return __s
 #endif
 
 template <int NN, int NQ, int NV, int CPB, bool CSR>
-__global__ void __launch_bounds__(NN *CPB, NN == 6 ? 5 : 2) k_cellmat(GgArgs a) {
+#ifndef GG_CM_MINB
+#define GG_CM_MINB 4   // resident CTAs per SM the register allocation of the triangle instance aims at (5: 128 registers with a
+                       // spilled loop variable whose reload cost 16 % of the samples; measured 7.08 vs 6.85 ms)
+#endif
+#ifndef GG_CM_UNROLL
+#define GG_CM_UNROLL 1  // unrolling of the trial-node loop
+#endif
+__global__ void __launch_bounds__(NN *CPB, NN == 6 ? GG_CM_MINB : 2) k_cellmat(GgArgs a) {
   using L = GgLayout<NN>;
   using Cell = GgCell<NN, NQ>;
   using Smem = GgSmem<NN, NQ, NV, CPB>;
   static_assert(sizeof(Cell) % 16 == 8, "odd number of doubles per cell");
   static_assert(NQ <= NN, "one thread per quadrature point");
   static_assert((CPB * (3 * NN + 3) * 4) % 16 == 0 && (CPB * NV * 4) % 16 == 0 && (CPB * 6 * NN * 2) % 16 == 0, "16-byte batch copies");
-  constexpr int LD = L::LD, NT = NN * CPB;
+  constexpr int LD = L::LD, NT = NN * CPB, UNR = GG_CM_UNROLL;
   GG_SMEM(Smem, smp);
   Smem &sm = *smp;
   const int tid = threadIdx.x, lc = tid / NN, it = tid - lc * NN;
@@ -306,8 +316,9 @@ __global__ void __launch_bounds__(NN *CPB, NN == 6 ? 5 : 2) k_cellmat(GgArgs a) 
     cr[NN + it] = r1;
     cr[2 * NN + 3 + it] = rT;
     if (it < 3) {
+      cr[2 * NN + it] = rP;  // (never read: keeps the 32-byte sectors of cr completely written)
       const int32_t gP = s.g[2 * NN + it];
-      if (gP > 0) a.b[gP - 1] = rP;  // discontinuous pressure: the cell's contribution is the whole entry
+      if (gP > 0 && c < a.nown) a.b[gP - 1] = rP;  // discontinuous pressure: the cell's contribution is the whole entry
     }
   }
   if (a.flags & GM_JACOBIAN) {
@@ -335,11 +346,11 @@ __global__ void __launch_bounds__(NN *CPB, NN == 6 ? 5 : 2) k_cellmat(GgArgs a) 
       }
       V0 *= js; V1 *= js;
       // the entry whose major is the velocity dof (it, a) and whose minor is pressure dof m goes to the intermediate ...
-      cm[it * LD + 2 * NN + m] = CSR ? -V0 : V0;
-      cm[(NN + it) * LD + 2 * NN + m] = CSR ? -V1 : V1;
+      cm[it * L::SU + 2 * NN + m] = CSR ? -V0 : V0;
+      cm[(NN + it) * L::SU + 2 * NN + m] = CSR ? -V1 : V1;
       // ... the one whose major is the pressure dof straight into its (complete) list
       const int32_t gP = s.g[2 * NN + m];
-      if (gP > 0) {
+      if (gP > 0 && c < a.nown) {
         const int64_t base = s.pb[m];
         const uint16_t p0 = s.gp[m * 2 * NN + it], p1 = s.gp[m * 2 * NN + NN + it];
         if (p0 != 0xFFFF) a.nz[base + p0] = CSR ? V0 : -V0;
@@ -348,7 +359,7 @@ __global__ void __launch_bounds__(NN *CPB, NN == 6 ? 5 : 2) k_cellmat(GgArgs a) 
     }
   }
   // ---- node pairs (it, ir): UU x4, UT x2, TU x2, TT x1 (Solver.jl:128-140)
-#pragma unroll 1
+#pragma unroll UNR
   for (int ir = 0; ir < NN; ++ir) {
     double uu[2][2] = {{0, 0}, {0, 0}}, tu[2] = {0, 0}, ggm = 0, ggw = 0, pu = 0, ww = 0;
 #pragma unroll
@@ -372,12 +383,12 @@ __global__ void __launch_bounds__(NN *CPB, NN == 6 ? 5 : 2) k_cellmat(GgArgs a) 
     const double tt = ggw + pu;
     // (test, trial) -> (minor, major) for CSC columns, (major, minor) for CSR rows
     if (!CSR) {
-      double *mU0 = cm + ir * LD, *mU1 = cm + (NN + ir) * LD, *mT = cm + L::OFF_T + ir * 3 * NN;
+      double *mU0 = cm + ir * L::SU, *mU1 = cm + (NN + ir) * L::SU, *mT = cm + L::OFF_T + ir * L::ST;
       mU0[it] = js * uu[0][0];      mU0[NN + it] = js * uu[1][0];  mU0[2 * NN + 3 + it] = js * tu[0];
       mU1[it] = js * uu[0][1];      mU1[NN + it] = js * uu[1][1];  mU1[2 * NN + 3 + it] = js * tu[1];
       mT[it] = js * (-RaPr * gv[0] * ww); mT[NN + it] = js * (-RaPr * gv[1] * ww); mT[2 * NN + it] = js * tt;
     } else {
-      double *mU0 = cm + it * LD, *mU1 = cm + (NN + it) * LD, *mT = cm + L::OFF_T + it * 3 * NN;
+      double *mU0 = cm + it * L::SU, *mU1 = cm + (NN + it) * L::SU, *mT = cm + L::OFF_T + it * L::ST;
       mU0[ir] = js * uu[0][0];      mU0[NN + ir] = js * uu[0][1];  mU0[2 * NN + 3 + ir] = js * (-RaPr * gv[0] * ww);
       mU1[ir] = js * uu[1][0];      mU1[NN + ir] = js * uu[1][1];  mU1[2 * NN + 3 + ir] = js * (-RaPr * gv[1] * ww);
       mT[ir] = js * tu[0];          mT[NN + ir] = js * tu[1];      mT[2 * NN + ir] = js * tt;
@@ -394,7 +405,8 @@ struct GgDesc {
   int64_t p0;        // list base in nzval
   int32_t j, isU;    // the dof (-1: padding record); velocity (1) or temperature (0) major
   int32_t len, cnt;  // list length; incident cells
-  int32_t e[10];     // the first ten (cell * LD + local) entries, ascending (more: adj[adjptr[j] + t])
+  uint32_t e[10];    // segment offsets (cell * NEC + offset of the major's segment) of the first ten incident cells, ascending
+                     // (more: from adj[adjptr[j] + t] = cell * LD + local)
 };
 
 // One warp per GROUP of four consecutive velocity / temperature major dofs (the record array is padded so that a group
@@ -408,6 +420,21 @@ struct GgDesc {
 // 18 majors of a triangle are visited at three far-apart times).  Lane l < 16 holds word l of records 0 / 2, lane
 // l >= 16 of records 1 / 3; entries are handed round by shuffles; the residual is a fixed-order butterfly over 8 lanes.
 #define GG_MPW 4  // majors per warp
+// segment offset of adjacency entry e = cell * LD + local (velocity or temperature major)
+template <int NN>
+__device__ __forceinline__ uint32_t gg_seg(int32_t e) {
+  using L = GgLayout<NN>;
+  const int32_t cc = e / L::LD;
+  const int M = e - cc * L::LD;
+  return (uint32_t)cc * L::NEC + (M < 2 * NN ? M * L::SU : L::OFF_T + (M - 2 * NN - 3) * L::ST);
+}
+// ... and back: cell * LD + local (index of the cell residual)
+template <int NN>
+__device__ __forceinline__ int64_t gg_seg_to_adj(uint32_t sg) {
+  using L = GgLayout<NN>;
+  const uint32_t cc = sg / L::NEC, r = sg - cc * L::NEC;
+  return (int64_t)cc * L::LD + (r < L::OFF_T ? r / L::SU : 2 * NN + 3 + (r - L::OFF_T) / L::ST);
+}
 template <int NN>
 __global__ void __launch_bounds__(GG_LWARPS * 32) k_lists(GgArgs a) {
   using L = GgLayout<NN>;
@@ -443,7 +470,7 @@ __global__ void __launch_bounds__(GG_LWARPS * 32) k_lists(GgArgs a) {
     int cg = cnt[0];
 #pragma unroll
     for (int q = 1; q < GG_MPW; ++q) cg = g == q ? cnt[q] : cg;
-    double v = t < cg ? a.cr[ew] : 0.0;
+    double v = t < cg ? a.cr[gg_seg_to_adj<NN>((uint32_t)ew)] : 0.0;
 #pragma unroll
     for (int m = 1; m < 8; m <<= 1) v += gg_shfl_xor(v, m);
 #pragma unroll
@@ -451,7 +478,7 @@ __global__ void __launch_bounds__(GG_LWARPS * 32) k_lists(GgArgs a) {
       if (cnt[q] > 8) {  // (uniform)
         const int64_t a0 = a0_of(q);
         for (int tt = 8; tt < cnt[q]; ++tt) {
-          const int32_t e = tt < 10 ? gg_shfl_i(w[q >> 1], (q & 1) * 16 + 6 + tt) : a.adj[a0 + tt];
+          const int64_t e = tt < 10 ? gg_seg_to_adj<NN>((uint32_t)gg_shfl_i(w[q >> 1], (q & 1) * 16 + 6 + tt)) : (int64_t)a.adj[a0 + tt];
           if (lane == 8 * q) v += a.cr[e];
         }
       }
@@ -471,16 +498,13 @@ __global__ void __launch_bounds__(GG_LWARPS * 32) k_lists(GgArgs a) {
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
         const int tt = d + t;
-        int32_t e = gg_shfl_i(w[g >> 1], (g & 1) * 16 + (tt < 10 ? 6 + tt : 0));
-        if (tt >= 10 && tt < cnt[g]) e = a.adj[a0_of(g) + tt];  // (uniform branch)
+        uint32_t sg = (uint32_t)gg_shfl_i(w[g >> 1], (g & 1) * 16 + (tt < 10 ? 6 + tt : 0));
+        if (tt >= 10 && tt < cnt[g]) sg = gg_seg<NN>(a.adj[a0_of(g) + tt]);  // (uniform branch)
         pos[g][t] = 0xFFFF;
         v[g][t] = 0;
         if (tt < cnt[g] && slot) {
-          const int32_t cc = e / LD;
-          const int M = e - cc * LD;
-          const int o = (isU ? M * LD : L::OFF_T + (M - 2 * NN - 3) * 3 * NN) + lane;
-          pos[g][t] = a.grank[(int64_t)cc * L::NEC + o];
-          v[g][t] = a.cm[(int64_t)cc * L::NEC + o];
+          pos[g][t] = a.grank[sg + lane];
+          v[g][t] = a.cm[sg + lane];
         }
       }
     }

@@ -50,6 +50,8 @@ struct gm_handle {
   int32_t *g_adj = nullptr;
   uint16_t *g_rank = nullptr, *g_rankp = nullptr;
   void *gather = nullptr;  // gm_gather: workspaces + device copy of the constants
+  int64_t n_own_cells = 0;        // unstructured partition: own cells first, then ghosts (== ncells on one GPU)
+  int64_t *ghost_ids = nullptr;   // [ncells - n_own_cells] global ids of the ghost cells
   // staging for the host API
   double *d_x = nullptr, *d_b = nullptr, *d_nz = nullptr;
   int64_t d_nz_cap = 0;

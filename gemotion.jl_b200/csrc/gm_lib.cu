@@ -122,10 +122,18 @@ extern "C" int gm_create(const gm_desc *d, gm_handle **out) {
       return GM_ERR_ARG;
     }
   } else if (d->ghost_lo || d->ghost_hi) {
-    gm_set_error("gm_create: row-block partition is implemented for Cartesian meshes only");
+    gm_set_error("gm_create: ghost ROWS describe Cartesian row blocks; unstructured meshes are partitioned by cell ranges (n_own_cells, ghost_cell_ids)");
     return GM_ERR_ARG;
   } else if (!d->coords || !d->cell_vertices || !d->dgphi || d->nverts <= 0) {
     gm_set_error("gm_create: unstructured mesh needs coords, cell_vertices and dgphi");
+    return GM_ERR_ARG;
+  }
+  if (d->n_own_cells < 0 || d->n_own_cells > d->ncells || (d->n_own_cells > 0 && d->n_own_cells < d->ncells && !d->ghost_cell_ids)) {
+    gm_set_error("gm_create: inconsistent cell partition (n_own_cells / ghost_cell_ids)");
+    return GM_ERR_ARG;
+  }
+  if (d->n_own_cells > 0 && d->n_own_cells < d->ncells && (d->cartesian || d->path == GM_PATH_SCATTER || d->path == GM_PATH_CART)) {
+    gm_set_error("gm_create: ghost cells need the gather path on an unstructured description");
     return GM_ERR_ARG;
   }
   if (d->layout != GM_LAYOUT_CSC && d->layout != GM_LAYOUT_CSR) { gm_set_error("gm_create: bad layout"); return GM_ERR_ARG; }
@@ -214,6 +222,8 @@ extern "C" int gm_create(const gm_desc *d, gm_handle **out) {
       TRY(gm_upload(h, &h->cellv, cv.data(), (int64_t)cv.size()));
     }
     if (d->path == GM_PATH_SCATTER) TRY(gm_color_generic(h, d));
+    h->n_own_cells = d->n_own_cells > 0 ? d->n_own_cells : h->ncells;
+    if (h->n_own_cells < h->ncells) TRY(gm_upload(h, &h->ghost_ids, d->ghost_cell_ids, h->ncells - h->n_own_cells));
   } else {
     h->ncolors = 4;
   }
@@ -235,6 +245,8 @@ extern "C" int gm_create(const gm_desc *d, gm_handle **out) {
   h->d.coords = nullptr; h->d.cell_vertices = nullptr; h->d.cell_dofs_u = h->d.cell_dofs_p = h->d.cell_dofs_t = nullptr;
   h->d.diri_u = h->d.diri_p = h->d.diri_t = nullptr;
   h->d.w = h->d.phi = h->d.dphi = h->d.psi = h->d.dgphi = nullptr;
+  h->d.ghost_cell_ids = nullptr;
+  if (h->n_own_cells == 0) h->n_own_cells = h->ncells;
   *out = h;
   return GM_OK;
 }
@@ -248,7 +260,7 @@ extern "C" void gm_destroy(gm_handle *h) {
   gm_gather_destroy(h);
   cudaFree(h->gdofs); cudaFree(h->dvals); cudaFree(h->coords); cudaFree(h->cellv);
   cudaFree(h->ptr); cudaFree(h->idx); cudaFree(h->rank); cudaFree(h->color_cells);
-  cudaFree(h->d_x); cudaFree(h->d_b); cudaFree(h->d_nz);
+  cudaFree(h->d_x); cudaFree(h->d_b); cudaFree(h->d_nz); cudaFree(h->ghost_ids);
   for (int k = 0; k < 4; ++k)
     if (h->ev[k]) cudaEventDestroy(h->ev[k]);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);

@@ -131,10 +131,10 @@ __global__ void k_rows(int64_t n, int nn, const int32_t *__restrict__ g, const i
       if (rank) rank[(c * ld + l) * ld + M] = rk;
       if (grank && gm_touched(fM, gm_field_of(l, nn))) {
         // compact major-major layout of the gather path (gm_gather_kernel.cuh): [U majors][T majors]; P majors apart
-        const int offT = 2 * nn * ld, nec = offT + nn * 3 * nn;
+        const int su = ld, st = 3 * nn, offT = 2 * nn * su, nec = offT + nn * st;
         const int s = (fM == 2 && l >= 2 * nn) ? l - 3 : l;
         if (fM == 1) grankp[c * 6 * nn + (M - 2 * nn) * 2 * nn + s] = rk;
-        else grank[c * nec + (fM == 0 ? M * ld : offT + (M - 2 * nn - 3) * 3 * nn) + s] = rk;
+        else grank[c * nec + (fM == 0 ? M * su : offT + (M - 2 * nn - 3) * st) + s] = rk;
       }
     }
   }

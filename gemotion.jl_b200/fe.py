@@ -426,8 +426,9 @@ class Spaces:
     cell_dofs_p: np.ndarray     # [nc,3] signed 1-based; last dof of the last cell is fixed (-1)
     n_free: np.ndarray          # [3] int64 (U,P,T)
     diri_p: np.ndarray          # [1] = 0.0
-    cells: Optional[slice] = None   # local cell range of a multi-GPU row block (None: all cells)
+    cells: Optional[slice] = None   # local cell range of a multi-GPU row block, or local cell ids (own + ghost) of an unstructured partition (None: all cells)
     rows: Optional[tuple] = None    # (r0, r1, ghost_lo, ghost_hi) cell rows owned by this rank
+    part: Optional[tuple] = None    # (c0, c1, ghost cell ids) of a contiguous-cell-range partition of an unstructured mesh
 
     @property
     def n_total(self):
@@ -472,6 +473,48 @@ def build_rank_spaces(model: "CartesianModel", bc_V, bc_Ttags, bc_Texpr, rank: i
     sp = build_spaces(model, bc_V, bc_Ttags, bc_Texpr, cells=sl)
     sp.rows = (r0, r1, glo, ghi)
     return sp
+
+
+def cell_block(model: DiscreteModel, rank: int, nranks: int):
+    """Unstructured meshes ("contiguous ranges"): rank owns the cells [c0, c1); its GHOSTS are the other ranks'
+    cells that share a vertex (hence possibly a P2 node) with one of them, ascending.  Returns (c0, c1, ghosts)."""
+    nc = model.ncells
+    c0, c1 = (nc * rank) // nranks, (nc * (rank + 1)) // nranks
+    mark = np.zeros(model.nverts, dtype=bool)
+    mark[model.cell_vertices[c0:c1].reshape(-1)] = True
+    touch = mark[model.cell_vertices].any(axis=1)
+    touch[c0:c1] = False
+    return c0, c1, np.nonzero(touch)[0].astype(np.int64)
+
+
+def build_rank_spaces_cells(model: DiscreteModel, bc_V, bc_Ttags, bc_Texpr, rank: int, nranks: int) -> Spaces:
+    """Spaces of one rank of a contiguous-cell-range partition of an unstructured mesh: global dof ids, local cell tables
+    (own cells, then ghost cells).  `sp.part` = (c0, c1, ghosts)."""
+    c0, c1, ghosts = cell_block(model, rank, nranks)
+    cells = np.concatenate([np.arange(c0, c1, dtype=np.int64), ghosts])
+    sp = build_spaces(model, bc_V, bc_Ttags, bc_Texpr, cells=cells)
+    sp.part = (c0, c1, ghosts)
+    return sp
+
+
+def owned_dofs_cells(sp: Spaces) -> np.ndarray:
+    """0-based global free-dof ids owned by the rank of `sp` (build_rank_spaces_cells): a dof belongs to the rank of its
+    lowest-numbered incident cell.  The local tables hold every incident cell of every dof of an own cell."""
+    c0, c1, ghosts = sp.part
+    gid = np.concatenate([np.arange(c0, c1, dtype=np.int64), ghosts])
+    off = sp.offsets
+    out = []
+    for tab, o in ((sp.U.cell_dofs, off[0]), (sp.cell_dofs_p, off[1]), (sp.T.cell_dofs, off[2])):
+        d = tab.astype(np.int64)
+        g = np.broadcast_to(gid[:, None], d.shape)[d > 0]
+        ids = d[d > 0] - 1 + o
+        order = np.lexsort((g, ids))
+        ids, g = ids[order], g[order]
+        first = np.ones(ids.size, dtype=bool)
+        first[1:] = ids[1:] != ids[:-1]
+        sel = first & (g >= c0) & (g < c1)
+        out.append(ids[sel])
+    return np.concatenate(out)
 
 
 # --------------------------------------------------------------------------------------
@@ -616,7 +659,9 @@ def interface_dofs(sp: Spaces, side: int) -> np.ndarray:
 
 
 def owned_dofs(sp: Spaces) -> np.ndarray:
-    """Owner-computes rule: a dof belongs to the lowest row block touching it."""
+    """Owner-computes rule: a dof belongs to the lowest row block (cell range) touching it."""
+    if getattr(sp, "part", None) is not None:
+        return np.sort(owned_dofs_cells(sp))
     if getattr(sp, "rows", None) is None:
         return np.arange(sp.n_total, dtype=np.int64)
     r0, r1, glo, ghi = sp.rows

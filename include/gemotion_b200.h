@@ -129,6 +129,14 @@ typedef struct gm_desc {
   /* structured path: kernel generation (gm_kernel) and quad columns per x-chunk (0 = chosen from the grid size; tests
    * force 32 / 128 / 256 to put chunk seams on small meshes) */
   int32_t kernel, xchunk;
+  /* Unstructured meshes on several GPUs (GM_PATH_GATHER): contiguous global cell ranges per rank.  The first
+   * n_own_cells cells of the tables are this rank's cells cell_begin .. cell_begin + n_own_cells - 1; the remaining
+   * ncells - n_own_cells cells are GHOSTS -- copies of the other ranks' cells that share a dof with an own cell, their global
+   * ids in ghost_cell_ids.  A dof belongs to the rank of its lowest-numbered incident cell; a rank assembles the complete
+   * lists of its dofs from its own and ghost cells, so there is NO exchange step (ghost cell matrices are recomputed).
+   * Lists / residual entries of dofs the rank does not own are left undefined.  0 / NULL: all cells are own cells. */
+  int64_t n_own_cells;
+  const int64_t *ghost_cell_ids; /* [ncells - n_own_cells] */
 } gm_desc;
 
 /* Timings of the last gm_assemble / gm_assemble_device call, milliseconds, CUDA events on the

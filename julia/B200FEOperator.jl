@@ -35,6 +35,7 @@ struct GmDesc
   cell_begin::Int64; ncells_global::Int64
   ghost_lo::Int32; ghost_hi::Int32
   kernel::Int32; xchunk::Int32
+  n_own_cells::Int64; ghost_cell_ids::Ptr{Int64}   # unstructured partition over several GPUs (0 / NULL: all cells are own cells)
 end
 
 gm_check(rc) = rc == 0 || error("gemotion_b200: " * unsafe_string(ccall((:gm_last_error, LIB), Cstring, ())))
@@ -128,7 +129,8 @@ mutable struct B200FEOperator <: FEOperator
                         pointer(t.w), pointer(t.phi), pointer(t.dphi), pointer(t.psi), pointer(t.dgphi),
                         Int32(device), Int32(0),                              # GM_PATH_AUTO
                         Int32(0), Int32(1), Int64(0), Int64(t.ncells), Int32(0), Int32(0),   # single GPU: rank 0 of 1
-                        Int32(0), Int32(0)))                                  # GM_KERNEL_AUTO, chunk chosen by the library
+                        Int32(0), Int32(0),                                   # GM_KERNEL_AUTO, chunk chosen by the library
+                        Int64(0), Ptr{Int64}(C_NULL)))                        # no ghost cells
       gm_check(ccall((:gm_create, LIB), Cint, (Ref{GmDesc}, Ref{Ptr{Cvoid}}), desc, href))
     end
     op.handle = href[]

@@ -64,7 +64,8 @@ class Oracle:
         r = sp.ref
         c = np.ascontiguousarray
         self._keep = dict(
-            coords=c(m.vertex_coords, dtype=np.float64), cv=c(m.cell_vertices, dtype=np.int32),
+            coords=c(m.vertex_coords, dtype=np.float64),
+            cv=c(m.cell_vertices if (m.cartesian or getattr(sp, "cells", None) is None) else m.cell_vertices[sp.cells], dtype=np.int32),
             du=c(sp.U.cell_dofs, dtype=np.int32), dp=c(sp.cell_dofs_p, dtype=np.int32),
             dt=c(sp.T.cell_dofs, dtype=np.int32),
             vu=c(sp.U.diri_values if sp.U.diri_values.size else np.zeros(1)),

@@ -50,10 +50,10 @@ static int run(GgArgs a, bool csr, int grid) {
       const int64_t a0 = a.adjptr[j];
       d.p0 = a.ptr[j]; d.j = (int32_t)j;
       d.len = (int32_t)(a.ptr[j + 1] - d.p0); d.cnt = (int32_t)(a.adjptr[j + 1] - a0);
-      for (int t = 0; t < 10; ++t) d.e[t] = t < d.cnt ? a.adj[a0 + t] : 0;
+      for (int t = 0; t < 10; ++t) d.e[t] = t < d.cnt ? gg_seg<NN>(a.adj[a0 + t]) : 0;
       maxlen = std::max(maxlen, (int)d.len);
     }
-    if (wg % GG_MPW == 0) order[wg / GG_MPW] = {real && d.cnt > 0 ? ((d.e[0] / ld) / 8) * 4 + (wg < nUp ? 0 : 2) + (d.cnt >= 4 ? 0 : 1) : 0x7fffffff, (int32_t)(wg / GG_MPW)};  // (windows of 8 cells here)
+    if (wg % GG_MPW == 0) order[wg / GG_MPW] = {real && d.cnt > 0 ? ((a.adj[a.adjptr[j]] / ld) / 8) * 4 + (wg < nUp ? 0 : 2) + (d.cnt >= 4 ? 0 : 1) : 0x7fffffff, (int32_t)(wg / GG_MPW)};  // (windows of 8 cells here)
   }
   std::stable_sort(order.begin(), order.end(), [](auto &x, auto &y) { return x.first < y.first; });
   for (int64_t g = 0; g < ngroup; ++g)
@@ -85,7 +85,7 @@ extern "C" int emu_gather_run(int nn, int64_t ncells, int64_t nU, int64_t oT, in
   // poisoned workspaces: an entry k_cellmat does not write, or k_lists reads from the wrong place, shows up as a huge number
   std::vector<double> cm((size_t)(ncells * nec), 1e300), cr((size_t)(ncells * ld), 1e300);
   GgArgs a;
-  a.ncells = ncells; a.nU = nU; a.oT = oT; a.n = n; a.gc = &c;
+  a.ncells = ncells; a.nown = ncells; a.nU = nU; a.oT = oT; a.n = n; a.gc = &c;
   a.gdofs = gdofs; a.dvals = dvals; a.coords = coords; a.cellv = cellv; a.ptr = ptr; a.grank = grank; a.grankp = grankp; a.adjptr = adjptr; a.adj = adj;
   a.x = x; a.cm = cm.data(); a.cr = cr.data(); a.nz = nz; a.b = b; a.flags = flags;
   return nn == 9 ? run<9, 4, 4>(a, csr != 0, grid) : run<6, 3, 3>(a, csr != 0, grid);

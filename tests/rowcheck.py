@@ -55,6 +55,16 @@ def sample_rows(sp, nrandom=2000, seed=7, strip=8, chunks=(128, 256), extra_rows
             for f in range(3):
                 hi = off[f] + sp.n_free[f]
                 picked.append(np.arange(max(off[f], hi - 40), hi, dtype=np.int64))
+    elif getattr(sp, "part", None) is not None:  # one rank of a cell-range partition: owned dofs only, plus those next to the range ends
+        from _pkg import gm
+        own = gm.fe.owned_dofs(sp)
+        picked.append(own[rng.integers(0, own.size, nrandom)])
+        c0, c1, _ = sp.part
+        nloc = c1 - c0
+        edge_cells = np.unique(np.clip(np.concatenate([np.arange(0, 40), np.arange(nloc - 40, nloc)]), 0, nloc - 1))
+        ids = np.concatenate([sp.U.cell_dofs[edge_cells].astype(np.int64).reshape(-1), (sp.cell_dofs_p[edge_cells].astype(np.int64) + off[1] * (sp.cell_dofs_p[edge_cells] > 0)).reshape(-1),
+                              (sp.T.cell_dofs[edge_cells].astype(np.int64) + off[2] * (sp.T.cell_dofs[edge_cells] > 0)).reshape(-1)])
+        picked.append(np.intersect1d(ids[ids > 0] - 1, own))
     else:
         picked.append(rng.integers(0, n, nrandom))
     rows = np.unique(np.concatenate(picked))

@@ -55,8 +55,9 @@ def gather_tables(g, nn, ptr, idx, n):
     nc, ld = g.shape
     field = np.array([0] * (2 * nn) + [1] * 3 + [2] * nn)
     touch = np.array([[1, 1, 1], [1, 0, 0], [1, 0, 1]], dtype=bool)
-    off_t = 2 * nn * ld
-    nec = off_t + nn * 3 * nn
+    su, st = ld, 3 * nn   # segment lengths of a velocity / temperature major
+    off_t = 2 * nn * su
+    nec = off_t + nn * st
     grank = np.full((nc, nec), 0xFFFF, dtype=np.uint16)
     grankp = np.full((nc, 6 * nn), 0xFFFF, dtype=np.uint16)
     adj = [[] for _ in range(n)]
@@ -68,7 +69,7 @@ def gather_tables(g, nn, ptr, idx, n):
             adj[gM - 1].append(c * ld + M)
             lst = idx[ptr[gM - 1]:ptr[gM]]
             fM = field[M]
-            tab, off = (grankp, (M - 2 * nn) * 2 * nn) if fM == 1 else (grank, M * ld if fM == 0 else off_t + (M - 2 * nn - 3) * 3 * nn)
+            tab, off = (grankp, (M - 2 * nn) * 2 * nn) if fM == 1 else (grank, M * su if fM == 0 else off_t + (M - 2 * nn - 3) * st)
             for l in range(ld):
                 if not touch[fM, field[l]]:
                     continue

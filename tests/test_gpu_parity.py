@@ -423,3 +423,50 @@ def test_config3_annulus_kuehn_size(gm, gpu_lib):
     assert info["active_path"] == gm.capi.GM_PATH_GATHER
     info = _check(gm, sp, dict(Pr=0.706, Ra=4.7e4, n=1.0), "csc", gm.capi.GM_PATH_SCATTER, x)
     assert info["active_path"] == gm.capi.GM_PATH_SCATTER and info["ncolors"] >= 6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nranks", [2, 3])
+@pytest.mark.parametrize("layout", ["csc", "csr"])
+def test_cell_range_partition_emulated_on_one_gpu(gm, gpu_lib, nranks, layout):
+    """Unstructured meshes on several GPUs (gather path): contiguous cell ranges + ghost cells, no exchange step.  Every rank's
+    handle is created on this GPU in turn; the lists and residual entries of the dofs it owns must equal the global oracle's,
+    the owned sets must partition the dofs, and gm_info.n_owned must agree with the host-side ownership rule."""
+    import torch
+    capi = gm.capi
+    model = fe.square_tri_model(9, jitter=0.25, seed=3)
+    spg = cases.spaces(model, cases.TURAN)
+    prm = dict(Pr=100.0, Ra=1e5, n=1.4, jac_scaling=1e-3)
+    x = fe.splitmix_iterate(spg.n_total, 4321)
+    orc = Oracle(spg, **prm)
+    optr, oidx = orc.pattern(layout)
+    onz, ob = orc.assemble(x, layout)
+    blocks_nz, blocks_b = cases.nz_blocks(spg, optr, oidx), cases.res_blocks(spg)
+    got_nz, got_b = np.full(onz.size, np.nan), np.full(ob.size, np.nan)
+    seen = np.zeros(spg.n_total, dtype=np.int32)
+    for r in range(nranks):
+        sp = fe.build_rank_spaces_cells(model, cases.TURAN["V"], cases.TURAN["Ttags"], cases.TURAN["Texpr"], r, nranks)
+        assert sp.part[2].size > 0  # (ghost cells)
+        h = capi.Handle(sp, layout=layout, path=capi.GM_PATH_GATHER, rank=r, nranks=nranks)
+        try:
+            h.set_params(**prm)
+            nnz_local = h.pattern()
+            dx = torch.from_numpy(x).cuda()
+            dnz = torch.full((nnz_local,), float("nan"), dtype=torch.float64, device="cuda")
+            db = torch.full((spg.n_total,), float("nan"), dtype=torch.float64, device="cuda")
+            torch.cuda.synchronize()
+            h.assemble_device(dx.data_ptr(), dnz.data_ptr(), db.data_ptr(), capi.GM_JACOBIAN | capi.GM_RESIDUAL, sync=True)
+            own = fe.owned_dofs(sp)
+            assert h.info()["n_owned"] == own.size
+            ptr, idx, val, b = h.get_rows(own, dnz.data_ptr(), db.data_ptr())
+            for k, dof in enumerate(own):
+                lo, hi = optr[dof], optr[dof + 1]
+                assert np.array_equal(idx[ptr[k]:ptr[k + 1]], oidx[lo:hi]), "owned list must be the global list"
+                got_nz[lo:hi] = val[ptr[k]:ptr[k + 1]]
+            got_b[own] = b
+            seen[own] += 1
+        finally:
+            h.close()
+    assert np.all(seen == 1)
+    assert cases.block_scaled_err(got_nz, onz, blocks_nz) <= TOL
+    assert cases.block_scaled_err(got_b, ob, blocks_b) <= TOL
