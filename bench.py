@@ -225,6 +225,14 @@ def main():
     nnz = h.pattern()
     t_pattern = time.perf_counter() - t0
     info = h.info()
+    nnz_tri_global = None
+    if world > 1 and args.mesh_type == "tri":
+        # global nnz = lists of the dofs each rank owns (its local pattern also holds the incomplete lists of the ghost cells' other dofs)
+        own_rows = gm.fe.owned_dofs(sp)
+        lens = np.diff(h.get_pattern(with_idx=False)[0])
+        t = torch.tensor([int(lens[own_rows].sum())], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        nnz_tri_global = int(t.item())
     if world > 1 and args.mesh_type != "tri":
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
@@ -412,6 +420,8 @@ def main():
     pk, pk_kind = peaks()
     N_ = args.mesh
     nnz_global = 684 * N_ * N_ - 1232 * N_ + 527 if world > 1 else nnz  # turan BC closed form, tested at small N
+    if nnz_tri_global is not None:
+        nnz_global = nnz_tri_global
     balg = algorithmic_bytes(sp, nnz_global) / world  # per-GPU share
     achieved = balg / (ms * 1e-3) / 1e9
     roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
@@ -421,7 +431,7 @@ def main():
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
-            tr_ = json.load(open(prof)).get(str(args.mesh))
+            tr_ = json.load(open(prof)).get(("tri%d" % args.mesh) if args.mesh_type == "tri" else str(args.mesh))
             # DRAM bytes of the dominant kernel from the committed `ncu --set full` capture of the 1-GPU run of this mesh
             # (profile-time figure, not re-measured in this run); a rank of an N-GPU run moves 1/N of it
             roof["traffic"] = tr_ / world if tr_ else None
