@@ -432,6 +432,8 @@ def main():
     if os.path.exists(prof):
         try:
             tr_ = json.load(open(prof)).get(("tri%d" % args.mesh) if args.mesh_type == "tri" else str(args.mesh))
+            if (args.mesh_type == "tri") != (info["active_path"] == 3) or (args.mesh_type != "tri" and info["active_path"] != 2):
+                tr_ = None  # (the committed captures are of the default path of each mesh type)
             # DRAM bytes of the dominant kernel from the committed `ncu --set full` capture of the 1-GPU run of this mesh
             # (profile-time figure, not re-measured in this run); a rank of an N-GPU run moves 1/N of it
             roof["traffic"] = tr_ / world if tr_ else None
