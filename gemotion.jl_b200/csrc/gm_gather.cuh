@@ -13,6 +13,12 @@ struct gm_gather {
   GgDesc *desc = nullptr;      // [ngroup][GG_MPW] records of the velocity / temperature majors, groups sorted by first incident cell
   int64_t ngroup = 0;
   int lstride = 96;
+  // launch set-up done once per handle (a handle lives on one device; the shared-memory opt-in is a per-device function attribute)
+  bool prepared = false;
+  int cm_per_sm = 1;
+  // parameters of the constant block on the device (re-uploaded only when gm_set_params changed them)
+  bool const_valid = false;
+  gm_params const_prm;
 };
 
 // one 64-byte record per velocity / temperature major (list base, length, incident cells) + the longest list;
@@ -152,14 +158,18 @@ static int gm_gather_after_pattern(gm_handle *h) {
 template <int NN, int NQ, int NV, int CPB, bool CSR>
 static int gm_gather_cellmat(gm_handle *h, GgArgs &a) {
   const size_t sm = sizeof(GgSmem<NN, NQ, NV, CPB>);
-  // (per device, not per process: set on every launch -- a handle on another device of the same process needs it too)
-  GM_CUDA(cudaFuncSetAttribute(k_cellmat<NN, NQ, NV, CPB, CSR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  int per_sm = 0;
-  GM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cellmat<NN, NQ, NV, CPB, CSR>, NN * CPB, sm));
-  if (per_sm < 1) per_sm = 1;
+  gm_gather *g = (gm_gather *)h->gather;
+  if (!g->prepared) {  // per device, not per process: every handle does it for its own device
+    GM_CUDA(cudaFuncSetAttribute(k_cellmat<NN, NQ, NV, CPB, CSR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    int per_sm = 0;
+    GM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cellmat<NN, NQ, NV, CPB, CSR>, NN * CPB, sm));
+    g->cm_per_sm = per_sm < 1 ? 1 : per_sm;
+    GM_CUDA(cudaFuncSetAttribute(k_lists<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * GG_LWARPS * GG_MPW * a.lstride)));
+    g->prepared = true;
+  }
   const int64_t nbatch = (h->ncells + CPB - 1) / CPB;
   a.nbatch = (int)nbatch;
-  const int64_t grid = std::min<int64_t>(nbatch, (int64_t)h->num_sms * per_sm);  // persistent: every CTA loops over batches
+  const int64_t grid = std::min<int64_t>(nbatch, (int64_t)h->num_sms * g->cm_per_sm);  // persistent: every CTA loops over batches
   k_cellmat<NN, NQ, NV, CPB, CSR><<<(unsigned)grid, NN * CPB, sm, h->stream>>>(a);
   return GM_OK;
 }
@@ -172,7 +182,6 @@ static int gm_gather_launch(gm_handle *h, GgArgs &a, int64_t *launches) {
   const int64_t nw = a.ngroup;  // warps
   if (nw > 0) {
     const size_t sml = sizeof(double) * GG_LWARPS * GG_MPW * a.lstride;
-    GM_CUDA(cudaFuncSetAttribute(k_lists<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sml));
     k_lists<NN><<<(unsigned)((nw + GG_LWARPS - 1) / GG_LWARPS), GG_LWARPS * 32, sml, h->stream>>>(a);
     ++*launches;
   }
@@ -183,10 +192,14 @@ static int gm_gather_launch(gm_handle *h, GgArgs &a, int64_t *launches) {
 static int gm_gather_run(gm_handle *h, const double *d_x, double *d_nz, double *d_b, unsigned flags, int64_t *launches) {
   gm_gather *g = (gm_gather *)h->gather;
   if (!g) { gm_set_error("gm_assemble: gather path without workspaces"); return GM_ERR_STATE; }
-  GmConst &c = h->hc;
-  c.Pr = h->prm.Pr; c.Ra = h->prm.Ra; c.n = h->prm.n; c.reg = h->prm.reg;
-  c.gx = h->prm.gx; c.gy = h->prm.gy; c.jac_scaling = h->prm.jac_scaling;
-  GM_CUDA(cudaMemcpyAsync(g->d_const, &c, sizeof(GmConst), cudaMemcpyHostToDevice, h->stream));  // (pageable source: staged before the call returns)
+  if (!g->const_valid || memcmp(&g->const_prm, &h->prm, sizeof(gm_params)) != 0) {
+    GmConst &c = h->hc;
+    c.Pr = h->prm.Pr; c.Ra = h->prm.Ra; c.n = h->prm.n; c.reg = h->prm.reg;
+    c.gx = h->prm.gx; c.gy = h->prm.gy; c.jac_scaling = h->prm.jac_scaling;
+    GM_CUDA(cudaMemcpyAsync(g->d_const, &c, sizeof(GmConst), cudaMemcpyHostToDevice, h->stream));  // (pageable source: staged before the call returns; ordered on the handle's stream)
+    g->const_prm = h->prm;
+    g->const_valid = true;
+  }
   GgArgs a;
   a.ncells = h->ncells;
   a.nown = h->n_own_cells;

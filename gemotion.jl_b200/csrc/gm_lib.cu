@@ -277,6 +277,8 @@ extern "C" int gm_set_params(gm_handle *h, double Pr, double Ra, double n, doubl
 
 extern "C" int gm_set_stream(gm_handle *h, void *stream) {
   if (!h) { gm_set_error("gm_set_stream: null handle"); return GM_ERR_ARG; }
+  GM_CUDA(cudaSetDevice(h->dev));
+  if (h->stream) GM_CUDA(cudaStreamSynchronize(h->stream));  // work and table uploads ordered on the old stream are complete before the switch
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   h->stream = (cudaStream_t)stream;
   h->own_stream = false;
