@@ -3,6 +3,8 @@
 Bars (BASELINE.json north_star): pattern bit-exact; nzval and residual within 1e-12 in the
 block-scaled sense of SURVEY 8a-note.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -371,6 +373,30 @@ def test_newton_through_the_plugin_matches_oracle_newton(gm, gpu_lib, n, bc, N):
         op.close()
     assert ref.f_converged and got.f_converged
     assert got.iterations == ref.iterations and got.f_calls == ref.f_calls
+    assert np.max(np.abs(got.x - ref.x)) <= 1e-10 * max(1.0, np.max(np.abs(ref.x)))
+
+
+def test_newton_config3_annulus_through_the_gather_path(gm, gpu_lib):
+    """Config 3 (validation-kuehn/kuehn.jl:30-52: concentric annulus, tags inner / outer / all, Pr=0.706, Ra=4.7e4, n=1) on a triangle
+    mesh read from a .msh file: Newton + BackTracking through the plug-in (generic gather path) takes the same iterations / residual
+    evaluations as through the oracle operator and ends at the same fields."""
+    import tempfile
+    from orc_operator import OracleOperator
+    from _pkg import gm as pkg
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "co-annulus.msh")
+        pkg.gmsh.write_msh(fe.annulus_model(nr=8, nt=48, jitter=0.2, seed=5), path, version="2.2")
+        sp = cases.spaces(pkg.gmsh.read_msh(path), cases.KUEHN)
+    prm = dict(Pr=0.706, Ra=4.7e4, n=1.0)
+    ref = gm.solver.newton(OracleOperator(sp, **prm), np.zeros(sp.n_total), ftol=1e-8, xtol=1e-50, iterations=60)
+    op = gm.operator.B200FEOperator(sp, **prm)
+    try:
+        assert op.h.info()["active_path"] == gm.capi.GM_PATH_GATHER
+        got = gm.solver.newton(op, np.zeros(sp.n_total), ftol=1e-8, xtol=1e-50, iterations=60)
+    finally:
+        op.close()
+    assert ref.f_converged and got.f_converged
+    assert (got.iterations, got.f_calls, got.g_calls) == (ref.iterations, ref.f_calls, ref.g_calls)
     assert np.max(np.abs(got.x - ref.x)) <= 1e-10 * max(1.0, np.max(np.abs(ref.x)))
 
 

@@ -26,9 +26,11 @@ RUNS = [
     ("turan-style 96x96 n=0.6 Ra=1e4 Pr=100 newton+BackTracking", 96, cases.TURAN, dict(Pr=100.0, Ra=1e4, n=0.6), "newton"),
     ("basak-style 40x40 n=1 trust_region (validation-basak/basak.jl:20-26, CI size)", 40, cases.SIMPLE, dict(Pr=0.7, Ra=1e3, n=1.0), "trust_region"),
 ]
+RUNS.append(("config3 validation-kuehn annulus, 2 x 18 x 128 generated triangles, Pr=0.706 Ra=4.7e4 n=1 newton+BackTracking (generic gather path)",
+             None, cases.KUEHN, dict(Pr=0.706, Ra=4.7e4, n=1.0), "newton"))
 out = []
 for name, N, bc, prm, method in RUNS:
-    sp = cases.cart(N, bc=bc)
+    sp = cases.cart(N, bc=bc) if N else cases.spaces(gm.fe.annulus_model(nr=18, nt=128, jitter=0.35, seed=7), bc)
     op = gm.operator.B200FEOperator(sp, **prm)
     t0 = time.perf_counter()
     drv = gm.solver.newton if method == "newton" else gm.solver.trust_region
