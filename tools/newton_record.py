@@ -28,8 +28,14 @@ RUNS = [
 ]
 RUNS.append(("config3 validation-kuehn annulus, 2 x 18 x 128 generated triangles, Pr=0.706 Ra=4.7e4 n=1 newton+BackTracking (generic gather path)",
              None, cases.KUEHN, dict(Pr=0.706, Ra=4.7e4, n=1.0), "newton"))
+only = sys.argv[1] if len(sys.argv) > 1 else None   # substring filter: the other runs keep their committed records
+recfile = os.path.join(ROOT, "profiles", "r02_newton_e2e.json")
 out = []
+if only and os.path.exists(recfile):
+    out = [r for r in json.load(open(recfile))["runs"] if only not in r["run"]]
 for name, N, bc, prm, method in RUNS:
+    if only and only not in name:
+        continue
     sp = cases.cart(N, bc=bc) if N else cases.spaces(gm.fe.annulus_model(nr=18, nt=128, jitter=0.35, seed=7), bc)
     op = gm.operator.B200FEOperator(sp, **prm)
     t0 = time.perf_counter()
@@ -46,4 +52,4 @@ for name, N, bc, prm, method in RUNS:
     out.append(rec)
     print(json.dumps(rec))
 json.dump({"what": "Newton end to end through the B200 plug-in; linear solves = SciPy SuperLU on the host", "runs": out},
-          open(os.path.join(ROOT, "profiles", "r02_newton_e2e.json"), "w"), indent=1)
+          open(recfile, "w"), indent=1)
