@@ -142,7 +142,7 @@ def run_reference(args, prm):
            "cpu_baseline": {"value": val, "unit": "Mcells/s", "cores": thr, "kind": "port", "sample": sample},
            "e2e": {"value": val, "unit": "Mcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out))
+    _emit(out)
 
 
 def workload_name(args):
@@ -459,8 +459,28 @@ def main():
                       "pattern_s": t_pattern, "tables_s": t_tables, "device_bytes": info["device_bytes"]},
            "roofline": roof, "verify": verify, "parts": parts, "cpu_baseline": cpu, "e2e": e2e, "e2e_note": e2e_note, "gpu_launches": int(launches_per_step * args.steps),
            "clocks": clocks, "ms_per_step_each": per, "checksum_abs_b": chk, "checksum_owned_abs_b": chk_owned}
-    print(json.dumps(out))
+    _emit(out)
 
+
+def _emit(out):
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    line = (json.dumps(out) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, line)
+    else:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+
+
+_REAL_STDOUT = None
 
 if __name__ == "__main__":
+    # Libraries print to file descriptor 1 behind Python's back (NCCL: "NCCL version ..." at the first communicator); the contract is
+    # ONE JSON line on stdout, so everything else written to fd 1 goes to stderr and the line is written to the saved descriptor.
+    try:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+    except OSError:
+        _REAL_STDOUT = None
     main()

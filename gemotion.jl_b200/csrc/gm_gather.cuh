@@ -27,8 +27,7 @@ struct gm_gather {
 // others get cnt = 0 (their lists are zero-filled, never summed) and are counted out of n_owned.
 __global__ void k_gg_desc(int64_t nU, int64_t oT, int64_t n, int ld, const int64_t *__restrict__ adjptr, const int32_t *__restrict__ adj,
                           const int64_t *__restrict__ ptr, int64_t nown, int64_t cell_begin, const int64_t *__restrict__ ghost_ids,
-                          GgDesc *__restrict__ desc, int32_t *__restrict__ key, int32_t *__restrict__ gid,
-                          int *__restrict__ maxlen, unsigned long long *__restrict__ nowned) {
+                          GgDesc *__restrict__ desc, int *__restrict__ maxlen, unsigned long long *__restrict__ nowned) {
   const int64_t wg = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t nUp = (nU + GG_MPW - 1) / GG_MPW * GG_MPW;
   if (wg >= (nUp + (n - oT) + GG_MPW - 1) / GG_MPW * GG_MPW) return;
@@ -66,12 +65,28 @@ __global__ void k_gg_desc(int64_t nU, int64_t oT, int64_t n, int ld, const int64
     atomicMax(maxlen, d.len);
   }
   desc[wg] = d;
-  if (wg % GG_MPW == 0) {
-    // windows of GG_WINDOW cells keep the reads of `cm` local; inside a window the long groups (vertex dofs) come first,
-    // so that the warps of a CTA finish together (a CTA's registers and shared memory are held until its slowest warp ends)
-    key[wg / GG_MPW] = real && d.cnt > 0 ? ((adj[adjptr[j]] / ld) / GG_WINDOW) * 4 + (wg < nUp ? 0 : 2) + (d.cnt >= 4 ? 0 : 1) : 0x7fffffff;
-    gid[wg / GG_MPW] = (int32_t)(wg / GG_MPW);
+}
+// Processing order of the groups: windows of GG_WINDOW cells keep the reads of `cm` local; inside a window the long groups
+// (vertex dofs) come first, so that the warps of a CTA finish together (a CTA's registers and shared memory are held until its
+// slowest warp ends).  Groups without any work -- padding, dofs this rank does not see or does not own: most of the global dof
+// range on a rank of a partitioned mesh -- get the largest key and are cut off after the sort (`nlive`).
+__global__ void k_gg_key(int64_t ngroup, int nec, const GgDesc *__restrict__ desc, int32_t *__restrict__ key, int32_t *__restrict__ gid,
+                         unsigned long long *__restrict__ nlive) {
+  const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (g >= ngroup) return;
+  uint32_t first = 0xFFFFFFFFu;
+  int maxcnt = 0;
+  for (int r = 0; r < GG_MPW; ++r) {
+    const GgDesc &d = desc[g * GG_MPW + r];
+    if (d.cnt > 0) {
+      const uint32_t cell = d.e[0] / (uint32_t)nec;
+      first = cell < first ? cell : first;
+      maxcnt = d.cnt > maxcnt ? d.cnt : maxcnt;
+    }
   }
+  key[g] = maxcnt > 0 ? (int32_t)((first / GG_WINDOW) * 4 + (desc[g * GG_MPW].isU ? 0 : 2) + (maxcnt >= 4 ? 0 : 1)) : 0x7fffffff;
+  gid[g] = (int32_t)g;
+  if (maxcnt > 0) atomicAdd(nlive, 1ull);
 }
 __global__ void k_gg_permute(int64_t ngroup, const int32_t *__restrict__ gid, const GgDesc *__restrict__ src, GgDesc *__restrict__ dst) {
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // one thread per 16-byte quarter record
@@ -116,7 +131,7 @@ static int gm_gather_after_pattern(gm_handle *h) {
   GgDesc *tmpd = nullptr;
   int32_t *key = nullptr, *gid = nullptr, *key2 = nullptr, *gid2 = nullptr;
   int *d_max = nullptr, hmax = 0;
-  unsigned long long *d_own = nullptr, hown = 0;
+  unsigned long long *d_own = nullptr, hown[2] = {0, 0};  // owned velocity / temperature dofs, groups with work
   void *tmp = nullptr;
   size_t tb = 0;
   rc = gm_dalloc(h, &g->desc, nrec);
@@ -128,11 +143,12 @@ static int gm_gather_after_pattern(gm_handle *h) {
   if (e == cudaSuccess) e = cudaMalloc(&gid2, 4 * g->ngroup);
   if (e == cudaSuccess) e = cudaMalloc(&d_max, sizeof(int));
   if (e == cudaSuccess) e = cudaMemsetAsync(d_max, 0, sizeof(int), h->stream);
-  if (e == cudaSuccess) e = cudaMalloc(&d_own, 8);
-  if (e == cudaSuccess) e = cudaMemsetAsync(d_own, 0, 8, h->stream);
+  if (e == cudaSuccess) e = cudaMalloc(&d_own, 16);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_own, 0, 16, h->stream);
   if (e == cudaSuccess) {
     k_gg_desc<<<gm_blocks(nrec, 256), 256, 0, h->stream>>>(h->off[1], h->off[2], h->n_total, h->ld, h->g_adjptr, h->g_adj, h->ptr, h->n_own_cells,
-                                                          h->d.cell_begin, h->ghost_ids, tmpd, key, gid, d_max, d_own);
+                                                          h->d.cell_begin, h->ghost_ids, tmpd, d_max, d_own);
+    k_gg_key<<<gm_blocks(g->ngroup, 256), 256, 0, h->stream>>>(g->ngroup, (int)nec, tmpd, key, gid, d_own + 1);
     cub::DeviceRadixSort::SortPairs(nullptr, tb, key, key2, gid, gid2, (int)g->ngroup, 0, 32, h->stream);
     e = cudaMalloc(&tmp, tb ? tb : 16);
   }
@@ -140,7 +156,7 @@ static int gm_gather_after_pattern(gm_handle *h) {
   if (e == cudaSuccess) {
     k_gg_permute<<<gm_blocks(nrec * 4, 256), 256, 0, h->stream>>>(g->ngroup, gid2, tmpd, g->desc);
     e = cudaMemcpyAsync(&hmax, d_max, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(&hown, d_own, 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hown, d_own, 16, cudaMemcpyDeviceToHost, h->stream);
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
   cudaFree(tmpd); cudaFree(key); cudaFree(gid); cudaFree(key2); cudaFree(gid2); cudaFree(d_max); cudaFree(d_own); cudaFree(tmp);
@@ -149,8 +165,9 @@ static int gm_gather_after_pattern(gm_handle *h) {
   if (h->ghost_ids) {  // owned dofs of a partitioned mesh: velocity / temperature majors counted above + the pressure dofs of the own cells
     int64_t np_own = 3 * h->n_own_cells;
     if (h->d.cell_begin + h->n_own_cells == h->d.ncells_global) np_own -= 1;  // (the fixed last pressure dof, Solver.jl:90)
-    h->n_owned = (int64_t)hown + np_own;
+    h->n_owned = (int64_t)hown[0] + np_own;
   }
+  g->ngroup = (int64_t)hown[1];  // the groups with work come first in the sorted record array
   g->lstride = (hmax + 3) & ~3;
   return GM_OK;
 }
