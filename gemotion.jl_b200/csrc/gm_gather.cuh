@@ -217,6 +217,11 @@ static int gm_gather_run(gm_handle *h, const double *d_x, double *d_nz, double *
     g->const_prm = h->prm;
     g->const_valid = true;
   }
+  if ((flags & GM_CHECK_FINITE) && h->ghost_ids) {
+    // partitioned mesh: the entries of dofs this rank does not own are never written; give the scan defined values
+    if ((flags & GM_JACOBIAN) && d_nz) GM_CUDA(cudaMemsetAsync(d_nz, 0, sizeof(double) * (size_t)h->nnz, h->stream));
+    if ((flags & GM_RESIDUAL) && d_b) GM_CUDA(cudaMemsetAsync(d_b, 0, sizeof(double) * (size_t)h->n_total, h->stream));
+  }
   GgArgs a;
   a.ncells = h->ncells;
   a.nown = h->n_own_cells;

@@ -484,6 +484,8 @@ def test_cell_range_partition_emulated_on_one_gpu(gm, gpu_lib, nranks, layout):
             h.assemble_device(dx.data_ptr(), dnz.data_ptr(), db.data_ptr(), capi.GM_JACOBIAN | capi.GM_RESIDUAL, sync=True)
             own = fe.owned_dofs(sp)
             assert h.info()["n_owned"] == own.size
+            # GM_CHECK_FINITE on a rank: entries of dofs it does not own are never assembled and must not trip the scan
+            h.assemble_device(dx.data_ptr(), dnz.data_ptr(), db.data_ptr(), capi.GM_JACOBIAN | capi.GM_RESIDUAL | capi.GM_CHECK_FINITE, sync=True)
             ptr, idx, val, b = h.get_rows(own, dnz.data_ptr(), db.data_ptr())
             for k, dof in enumerate(own):
                 lo, hi = optr[dof], optr[dof + 1]
