@@ -300,6 +300,25 @@ class CartesianModel(DiscreteModel):
         return ent
 
 
+class JitteredQuadModel(CartesianModel):
+    """An UNSTRUCTURED quadrilateral mesh (what Gridap holds for a recombined Gmsh mesh): the topology, numbering and labels of
+    the Cartesian model, interior vertices displaced by up to `jitter` of the cell size, `cartesian = False` -- so the bilinear
+    geometry map (a different Jacobian at every quadrature point) of the generic kernels is exercised; P2 edge / cell nodes sit
+    at the images of the reference nodes (edge midpoints, mean of the four vertices)."""
+    cartesian = False
+
+    def __init__(self, domain=(0.0, 1.0, 0.0, 1.0), partition=(6, 5), jitter=0.25, seed=0):
+        super().__init__(domain, partition)
+        nx, ny = self.partition
+        rng = np.random.default_rng(seed)
+        vi = np.tile(np.arange(nx + 1), ny + 1)
+        vj = np.repeat(np.arange(ny + 1), nx + 1)
+        interior = (vi > 0) & (vi < nx) & (vj > 0) & (vj < ny)
+        d = (rng.random((interior.sum(), 2)) - 0.5) * 2.0 * jitter * np.array(self.h)
+        self.vertex_coords = self.vertex_coords.copy()
+        self.vertex_coords[interior] += d
+
+
 class TriangleModel(DiscreteModel):
     """Triangle model with named tags, the shape GridapGmsh hands to the reference
     (examples/validation-kuehn/kuehn.jl:13-22).

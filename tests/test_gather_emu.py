@@ -122,6 +122,7 @@ MODELS = {
     "cart1x1": lambda: cases.cart(1, 1, bc=cases.SIMPLE),
     "sqtri16": lambda: cases.spaces(fe.square_tri_model(16, jitter=0.2, seed=5), cases.TURAN),   # 512 cells: 32 batches, 11 per CTA
     "fan14": lambda: cases.spaces(cases.fan_model(14), cases.FAN),                                # valence 14: list > 96, cnt > 10
+    "jquad6x5": lambda: cases.spaces(fe.JitteredQuadModel((0, 2, 0, 1), (6, 5), jitter=0.25, seed=2), cases.TURAN),   # bilinear geometry
     "cart12x8": lambda: cases.cart(12, 8, bc=cases.WAVE),                                       # 96 cells: 6 full batches
 }
 PARAMS = [dict(Pr=100.0, Ra=1e5, n=0.6), dict(Pr=0.706, Ra=4.7e4, n=1.0), dict(Pr=10.0, Ra=1e4, n=1.4, g=(0.3, -0.8), jac_scaling=1e-6)]

@@ -41,9 +41,11 @@ def test_golden_newton_62(gm):
 
 
 @pytest.mark.parametrize("n", [0.6, 1.0, 1.4])
-@pytest.mark.parametrize("kind", ["quad", "tri"])
+@pytest.mark.parametrize("kind", ["quad", "jquad", "tri"])
 def test_jacobian_is_derivative_of_residual(kind, n):
-    sp = cases.cart(5, 4, bc=cases.WAVE) if kind == "quad" else cases.spaces(fe.annulus_model(nr=3, nt=8, jitter=0.2), cases.KUEHN)
+    sp = (cases.cart(5, 4, bc=cases.WAVE) if kind == "quad" else
+          cases.spaces(fe.JitteredQuadModel((0, 1, 0, 1), (5, 4), jitter=0.25, seed=1), cases.WAVE) if kind == "jquad" else
+          cases.spaces(fe.annulus_model(nr=3, nt=8, jitter=0.2), cases.KUEHN))
     orc = Oracle(sp, Pr=7.0, Ra=300.0, n=n)
     rng = np.random.default_rng(0)
     x = rng.random(sp.n_total)
