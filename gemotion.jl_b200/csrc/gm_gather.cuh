@@ -88,6 +88,12 @@ __global__ void k_gg_key(int64_t ngroup, int nec, const GgDesc *__restrict__ des
   gid[g] = (int32_t)g;
   if (maxcnt > 0) atomicAdd(nlive, 1ull);
 }
+// The gather path writes the lists of the pressure majors straight from the one cell that owns them (P1-disc, `space=:P`,
+// Solver.jl:89-90): a pressure dof shared by several cells (a continuous pressure space) is not supported here.
+__global__ void k_gg_check_p(int64_t nP, int64_t oP, const int64_t *__restrict__ adjptr, int *__restrict__ bad) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t < nP && adjptr[oP + t + 1] - adjptr[oP + t] > 1) atomicExch(bad, 1);
+}
 __global__ void k_gg_permute(int64_t ngroup, const int32_t *__restrict__ gid, const GgDesc *__restrict__ src, GgDesc *__restrict__ dst) {
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // one thread per 16-byte quarter record
   if (t >= ngroup * GG_MPW * 4) return;
@@ -125,6 +131,21 @@ static int gm_gather_after_pattern(gm_handle *h) {
     return rc;
   }
   static_assert(sizeof(GgDesc) == 64, "one 64-byte record per major");
+  {
+    int *d_bad = nullptr, hbad = 0;
+    const int64_t nP = h->off[2] - h->off[1];
+    GM_CUDA(cudaMalloc(&d_bad, sizeof(int)));
+    cudaError_t eb = cudaMemsetAsync(d_bad, 0, sizeof(int), h->stream);
+    if (eb == cudaSuccess && nP > 0) k_gg_check_p<<<gm_blocks(nP, 256), 256, 0, h->stream>>>(nP, h->off[1], h->g_adjptr, d_bad);
+    if (eb == cudaSuccess) eb = cudaMemcpyAsync(&hbad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    if (eb == cudaSuccess) eb = cudaStreamSynchronize(h->stream);
+    cudaFree(d_bad);
+    if (eb != cudaSuccess) { gm_set_error("gm_pattern: %s", cudaGetErrorString(eb)); return GM_ERR_CUDA; }
+    if (hbad) {
+      gm_set_error("gm_pattern: the gather path needs a discontinuous pressure space (every pressure dof in exactly one cell, Solver.jl:89-90); use GM_PATH_SCATTER");
+      return GM_ERR_ARG;
+    }
+  }
   const int64_t nrec = ((h->off[1] + GG_MPW - 1) / GG_MPW * GG_MPW + (h->n_total - h->off[2]) + GG_MPW - 1) / GG_MPW * GG_MPW;
   g->ngroup = nrec / GG_MPW;
   if (g->ngroup == 0) return GM_OK;

@@ -499,3 +499,21 @@ def test_cell_range_partition_emulated_on_one_gpu(gm, gpu_lib, nranks, layout):
     assert np.all(seen == 1)
     assert cases.block_scaled_err(got_nz, onz, blocks_nz) <= TOL
     assert cases.block_scaled_err(got_b, ob, blocks_b) <= TOL
+
+
+def test_gather_path_rejects_a_shared_pressure_dof(gm, gpu_lib):
+    """The gather path writes pressure lists straight from their one cell (P1-disc, Solver.jl:89-90).  Tables in which two cells
+    share a pressure dof must be refused by gm_pattern (GM_ERR_ARG), not assembled wrongly; the scatter path takes them."""
+    import copy
+    sp = copy.copy(cases.spaces(fe.square_tri_model(4, jitter=0.2, seed=9), cases.TURAN))
+    sp.cell_dofs_p = sp.cell_dofs_p.copy()
+    sp.cell_dofs_p[1, 0] = sp.cell_dofs_p[0, 0]   # cells 0 and 1 now share a pressure dof (the id of cell 1's own dof stays unused)
+    h = gm.capi.Handle(sp, path=gm.capi.GM_PATH_GATHER)
+    try:
+        with pytest.raises(gm.capi.GmError) as ei:
+            h.pattern()
+        assert ei.value.code == -1 and "discontinuous pressure" in str(ei.value)
+    finally:
+        h.close()
+    x = fe.splitmix_iterate(sp.n_total, 3)
+    _check(gm, sp, PARAMS[0], "csc", gm.capi.GM_PATH_SCATTER, x)
