@@ -120,6 +120,7 @@ MODELS = {
     "annulus": lambda: cases.spaces(fe.annulus_model(nr=3, nt=12, jitter=0.3, seed=1), cases.KUEHN),
     "cart7x5": lambda: cases.cart(7, 5, bc=cases.TURAN),
     "cart1x1": lambda: cases.cart(1, 1, bc=cases.SIMPLE),
+    "sqtri1": lambda: cases.spaces(fe.square_tri_model(1), cases.TURAN),   # two triangles: two free velocity dofs, one ragged batch, one group per field
     "sqtri16": lambda: cases.spaces(fe.square_tri_model(16, jitter=0.2, seed=5), cases.TURAN),   # 512 cells: 32 batches, 11 per CTA
     "fan14": lambda: cases.spaces(cases.fan_model(14), cases.FAN),                                # valence 14: list > 96, cnt > 10
     "jquad6x5": lambda: cases.spaces(fe.JitteredQuadModel((0, 2, 0, 1), (6, 5), jitter=0.25, seed=2), cases.TURAN),   # bilinear geometry

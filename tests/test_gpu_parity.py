@@ -31,6 +31,7 @@ def _models():
     yield "annulus", cases.spaces(fe.annulus_model(nr=4, nt=16, jitter=0.3, seed=1), cases.KUEHN)
     yield "sqtri", cases.spaces(fe.square_tri_model(6, jitter=0.3, seed=2), cases.TURAN)
     yield "fan14", cases.spaces(cases.fan_model(14), cases.FAN)
+    yield "sqtri1", cases.spaces(fe.square_tri_model(1), cases.TURAN)   # two triangles
     yield "jquad7x5", cases.spaces(fe.JitteredQuadModel((0, 2, 0, 1), (7, 5), jitter=0.25, seed=2), cases.WAVE)   # unstructured quads: bilinear geometry
 
 
