@@ -279,6 +279,8 @@ def main():
     value = ncells_total / (ms * 1e-3) / 1e6
     # checksum of the result (also the D2H read of the step's result for the record)
     chk = float(d_b.abs().sum().item())
+    own_idx = gm.fe.owned_dofs(sp) if world > 1 else None   # (a rank's buffers are only defined on the dofs it owns)
+    chk_own_local = float(d_b[torch.from_numpy(own_idx).cuda()].abs().sum().item()) if world > 1 else chk
     chk_owned = None
     if args.mesh <= 1024:  # sum over OWNED residual entries: must not depend on the number of GPUs
         own = torch.from_numpy(gm.fe.owned_dofs(sp)).cuda()
@@ -361,7 +363,7 @@ def main():
 
     if not args.no_e2e:
         # the caller's own arrays (Julia: A.nzval, b, x), page-locked once with gm_host_register as INTEGRATION.md says
-        xn, nzn, bn = x_host, np.empty(nnz), np.empty(sp.n_total)
+        xn, nzn, bn = x_host, np.empty(nnz), np.zeros(sp.n_total)
         pinned = []
         try:
             for arr in (xn, nzn, bn):
@@ -388,7 +390,7 @@ def main():
         e2e = {"value": ncells_total / (e_ms * 1e-3) / 1e6, "unit": "Mcells/s", "ms_per_step": e_ms,
                "h2d_bytes_per_step": int(tt["h2d_bytes"]), "d2h_bytes_per_step": int(tt["d2h_bytes"]),
                "h2d_ms": tt["h2d_ms"], "kernel_ms": tt["kernel_ms"], "d2h_ms": tt["d2h_ms"], "steps": args.e2e_steps,
-               "checksum_match": bool(abs(float(np.abs(bn).sum()) - chk) <= 1e-9 * max(1.0, chk))}
+               "checksum_match": bool(abs(float(np.abs(bn if own_idx is None else bn[own_idx]).sum()) - chk_own_local) <= 1e-9 * max(1.0, chk_own_local))}
         # residual-only end to end (iterate H2D + residual D2H): the call a line search repeats
         ts = []
         for _ in range(args.e2e_steps + 1):

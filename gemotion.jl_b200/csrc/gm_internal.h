@@ -59,6 +59,8 @@ struct gm_handle {
   gm_times times;
   bool times_pending = false;  // kernel_ms / exchange_ms of the last device assembly not read back yet
   int64_t n_owned = 0;         // dofs owned by this rank (row blocks); 0: all
+  // host API on a rank of a partition: only the dof ranges its cells touch are copied (iterate in, residual out)
+  std::vector<std::pair<int64_t, int64_t>> xruns;  // [begin, end) runs, ascending; empty: everything
   int64_t device_bytes = 0;
 };
 

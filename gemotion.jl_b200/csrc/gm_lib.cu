@@ -229,6 +229,8 @@ extern "C" int gm_create(const gm_desc *d, gm_handle **out) {
   }
   TRY(gm_dalloc(h, &h->d_x, h->n_total));
   TRY(gm_dalloc(h, &h->d_b, h->n_total));
+  TRYC(cudaMemset(h->d_x, 0, sizeof(double) * (size_t)h->n_total));  // (entries no kernel writes / no copy fills stay finite)
+  TRYC(cudaMemset(h->d_b, 0, sizeof(double) * (size_t)h->n_total));
   // generic meshes: owner-computes gather unless the caller asks for the colour-ordered scatter
   h->active_path = d->path == GM_PATH_SCATTER ? GM_PATH_SCATTER : GM_PATH_GATHER;
   if (d->path < GM_PATH_AUTO || d->path > GM_PATH_GATHER) { gm_set_error("gm_create: bad path"); return fail(GM_ERR_ARG); }
@@ -285,6 +287,60 @@ extern "C" int gm_set_stream(gm_handle *h, void *stream) {
   return GM_OK;
 }
 
+// dof ranges touched by the local cells (a rank of a partition sees a fraction of the global numbering: Gridap numbers seven
+// groups -- U vertices / edges / cells, P, T vertices / edges / cells -- one after another, so a row block touches about seven
+// runs).  Runs closer than min(64 Ki, n / 256) dofs are merged; more than 64 runs -> one full copy.
+__global__ void k_mark_touched(int64_t nent, const int32_t *__restrict__ g, uint8_t *__restrict__ flag) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t < nent && g[t] > 0) flag[g[t] - 1] = 1;
+}
+__global__ void k_run_bounds(int64_t n, const uint8_t *__restrict__ flag, int cap, int *__restrict__ cnt, int64_t *__restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i > n) return;
+  const uint8_t cur = i < n ? flag[i] : 0, prev = i > 0 ? flag[i - 1] : 0;
+  if (cur != prev) {
+    const int k = atomicAdd(cnt, 1);
+    if (k < cap) out[k] = i;
+  }
+}
+static int gm_touched_runs(gm_handle *h) {
+  h->xruns.clear();
+  if (h->d.nranks <= 1) return GM_OK;
+  const int64_t n = h->n_total, nent = h->ncells * h->ld;
+  const int CAP = 8192;
+  uint8_t *flag = nullptr;
+  int *cnt = nullptr, hc = 0;
+  int64_t *out = nullptr;
+  std::vector<int64_t> hb;
+  cudaError_t e = cudaMalloc(&flag, (size_t)n + 1);
+  if (e == cudaSuccess) e = cudaMalloc(&cnt, sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&out, sizeof(int64_t) * CAP);
+  if (e == cudaSuccess) e = cudaMemsetAsync(flag, 0, (size_t)n + 1, h->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(cnt, 0, sizeof(int), h->stream);
+  if (e == cudaSuccess) {
+    k_mark_touched<<<gm_blocks(nent, 256), 256, 0, h->stream>>>(nent, h->gdofs, flag);
+    k_run_bounds<<<gm_blocks(n + 1, 256), 256, 0, h->stream>>>(n, flag, CAP, cnt, out);
+    e = cudaMemcpyAsync(&hc, cnt, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e == cudaSuccess && hc > 0 && hc <= CAP && (hc & 1) == 0) {
+    hb.resize((size_t)hc);
+    e = cudaMemcpy(hb.data(), out, sizeof(int64_t) * hc, cudaMemcpyDeviceToHost);
+  }
+  cudaFree(flag); cudaFree(cnt); cudaFree(out);
+  if (e != cudaSuccess) { gm_set_error("gm_pattern: %s", cudaGetErrorString(e)); return GM_ERR_CUDA; }
+  if (hb.empty()) return GM_OK;  // (nothing touched / too fragmented: full copies)
+  std::sort(hb.begin(), hb.end());
+  std::vector<std::pair<int64_t, int64_t>> runs;
+  const int64_t gap = std::max<int64_t>(16, std::min<int64_t>(65536, n / 256));
+  for (size_t k = 0; k + 1 < hb.size(); k += 2) {
+    if (!runs.empty() && hb[k] - runs.back().second < gap) runs.back().second = hb[k + 1];
+    else runs.emplace_back(hb[k], hb[k + 1]);
+  }
+  if (runs.size() <= 64) h->xruns = runs;
+  return GM_OK;
+}
+
 extern "C" int gm_pattern(gm_handle *h, int64_t *nnz) {
   if (!h) { gm_set_error("gm_pattern: null handle"); return GM_ERR_ARG; }
   GM_CUDA(cudaSetDevice(h->dev));
@@ -299,6 +355,8 @@ extern "C" int gm_pattern(gm_handle *h, int64_t *nnz) {
       rc = gm_gather_after_pattern(h);
       if (rc) return rc;
     }
+    rc = gm_touched_runs(h);
+    if (rc) return rc;
     if (h->d.ghost_lo || h->d.ghost_hi) {
       if (h->active_path != GM_PATH_CART) { gm_set_error("gm_pattern: row blocks need the structured path"); return GM_ERR_ARG; }
       rc = gm_multi_after_pattern(h);
@@ -501,10 +559,20 @@ extern "C" int gm_assemble(gm_handle *h, const double *x, double *nzval, double 
     int rc = gm_dalloc(h, &h->d_nz, h->nnz);
     if (rc) return rc;
     h->d_nz_cap = h->nnz;
+    GM_CUDA(cudaMemsetAsync(h->d_nz, 0, sizeof(double) * (size_t)h->nnz, h->stream));
   }
   int64_t launches = 0;
   GM_CUDA(cudaEventRecord(h->ev[0], h->stream));
-  GM_CUDA(cudaMemcpyAsync(h->d_x, x, sizeof(double) * (size_t)h->n_total, cudaMemcpyHostToDevice, h->stream));
+  int64_t xfer = 0;  // dofs copied each way (a rank of a partition: only the ranges its cells touch)
+  if (h->xruns.empty()) {
+    GM_CUDA(cudaMemcpyAsync(h->d_x, x, sizeof(double) * (size_t)h->n_total, cudaMemcpyHostToDevice, h->stream));
+    xfer = h->n_total;
+  } else {
+    for (const auto &r : h->xruns) {
+      GM_CUDA(cudaMemcpyAsync(h->d_x + r.first, x + r.first, sizeof(double) * (size_t)(r.second - r.first), cudaMemcpyHostToDevice, h->stream));
+      xfer += r.second - r.first;
+    }
+  }
   GM_CUDA(cudaEventRecord(h->ev[1], h->stream));
   int rc = gm_run(h, h->d_x, jac ? h->d_nz : nullptr, res ? h->d_b : nullptr, flags, &launches);
   if (rc) return rc;
@@ -514,7 +582,14 @@ extern "C" int gm_assemble(gm_handle *h, const double *x, double *nzval, double 
     if (rc) return rc;
   }
   if (jac) GM_CUDA(cudaMemcpyAsync(nzval, h->d_nz, sizeof(double) * (size_t)h->nnz, cudaMemcpyDeviceToHost, h->stream));
-  if (res) GM_CUDA(cudaMemcpyAsync(resid, h->d_b, sizeof(double) * (size_t)h->n_total, cudaMemcpyDeviceToHost, h->stream));
+  if (res) {
+    if (h->xruns.empty()) {
+      GM_CUDA(cudaMemcpyAsync(resid, h->d_b, sizeof(double) * (size_t)h->n_total, cudaMemcpyDeviceToHost, h->stream));
+    } else {  // entries outside the touched ranges are not this rank's: the caller's array keeps what it held there
+      for (const auto &r : h->xruns)
+        GM_CUDA(cudaMemcpyAsync(resid + r.first, h->d_b + r.first, sizeof(double) * (size_t)(r.second - r.first), cudaMemcpyDeviceToHost, h->stream));
+    }
+  }
   GM_CUDA(cudaEventRecord(h->ev[3], h->stream));
   GM_CUDA(cudaStreamSynchronize(h->stream));
   float a = 0, b = 0, c = 0;
@@ -523,8 +598,8 @@ extern "C" int gm_assemble(gm_handle *h, const double *x, double *nzval, double 
   GM_CUDA(cudaEventElapsedTime(&c, h->ev[2], h->ev[3]));
   h->times.h2d_ms = a; h->times.kernel_ms = b; h->times.d2h_ms = c;
   h->times.launches = launches;
-  h->times.h2d_bytes = 8 * h->n_total;
-  h->times.d2h_bytes = (jac ? 8 * h->nnz : 0) + (res ? 8 * h->n_total : 0);
+  h->times.h2d_bytes = 8 * xfer;
+  h->times.d2h_bytes = (jac ? 8 * h->nnz : 0) + (res ? 8 * xfer : 0);
   return GM_OK;
 }
 

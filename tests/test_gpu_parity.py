@@ -518,3 +518,43 @@ def test_gather_path_rejects_a_shared_pressure_dof(gm, gpu_lib):
         h.close()
     x = fe.splitmix_iterate(sp.n_total, 3)
     _check(gm, sp, PARAMS[0], "csc", gm.capi.GM_PATH_SCATTER, x)
+
+
+def test_host_api_on_a_partition_rank_copies_only_its_dof_ranges(gm, gpu_lib):
+    """gm_assemble (host arrays) on one rank of a cell-range partition: the iterate is read and the residual written only on the
+    dof ranges the rank's cells touch (gm_times.h2d_bytes < 8 n); owned entries equal the global oracle, entries outside the
+    touched ranges keep what the caller's array held."""
+    model = fe.square_tri_model(24, jitter=0.2, seed=6)
+    spg = cases.spaces(model, cases.TURAN)
+    prm = dict(Pr=100.0, Ra=1e5, n=0.6)
+    x = fe.splitmix_iterate(spg.n_total, 77)
+    orc = Oracle(spg, **prm)
+    optr, oidx = orc.pattern("csc")
+    onz, ob = orc.assemble(x, "csc")
+    nranks, r = 4, 2
+    sp = fe.build_rank_spaces_cells(model, cases.TURAN["V"], cases.TURAN["Ttags"], cases.TURAN["Texpr"], r, nranks)
+    h = gm.capi.Handle(sp, path=gm.capi.GM_PATH_GATHER, rank=r, nranks=nranks)
+    try:
+        h.set_params(**prm)
+        nnz_local = h.pattern()
+        nz, b = np.full(nnz_local, np.nan), np.full(spg.n_total, -7.0)
+        h.assemble(x, nz, b)
+        t = h.timing()
+        assert 0 < t["h2d_bytes"] < 8 * spg.n_total * 0.6          # a quarter of the mesh (+ ghosts), not the whole iterate
+        own = fe.owned_dofs(sp)
+        assert np.max(np.abs(b[own] - ob[own])) <= TOL * np.max(np.abs(ob))
+        touched = np.zeros(spg.n_total, dtype=bool)
+        for tab, o in ((sp.U.cell_dofs, sp.offsets[0]), (sp.cell_dofs_p, sp.offsets[1]), (sp.T.cell_dofs, sp.offsets[2])):
+            d = tab.astype(np.int64).reshape(-1)
+            touched[d[d > 0] - 1 + o] = True
+        gap = max(16, min(65536, spg.n_total // 256))   # (runs closer than this are merged into one copy)
+        far = ~np.convolve(touched.astype(np.int32), np.ones(2 * gap + 1, dtype=np.int32), mode="same").astype(bool)
+        assert far.sum() > spg.n_total // 4 and np.all(b[far] == -7.0)
+        # nzval through the host path: lists of a sample of owned dofs
+        lp, _ = h.get_pattern(with_idx=False)
+        for k, dof in enumerate(own[::7]):
+            got = nz[lp[dof]:lp[dof + 1]]
+            ref = onz[optr[dof]:optr[dof + 1]]
+            assert got.size == ref.size and np.max(np.abs(got - ref)) <= 1e-12 * max(1.0, np.max(np.abs(onz)))
+    finally:
+        h.close()
