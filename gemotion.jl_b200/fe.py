@@ -634,8 +634,8 @@ def square_tri_model(n=8, jitter=0.0, seed=0) -> TriangleModel:
     for j in range(n):
         for i in range(n):
             a, b, c, d = vid(i, j), vid(i + 1, j), vid(i, j + 1), vid(i + 1, j + 1)
-            if (i == 0 and j == 0) or (i == n - 1 and j == n - 1):
-                tris += [(a, b, c), (b, d, c)]  # diagonal b-c
+            if n > 1 and ((i == 0 and j == n - 1) or (i == n - 1 and j == 0)):
+                tris += [(a, b, c), (b, d, c)]  # diagonal b-c: with a-d the corner triangle would have two boundary edges
             else:
                 tris += [(a, b, d), (a, d, c)]  # diagonal a-d
     vi, vj = np.tile(np.arange(n + 1), n + 1), np.repeat(np.arange(n + 1), n + 1)

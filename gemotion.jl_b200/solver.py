@@ -284,6 +284,39 @@ def nu_bot_avg(sp, x, n_plot=100):
     return float(np.sum(out) / len(out))
 
 
+def nu_bot_avg_generic(sp, x, n_plot=100):
+    """The same functional on any mesh of the unit square (triangles: the cell with an edge on y = 0 that contains the sample
+    point, physical gradient through the affine map) -- used to compare the triangle discretisation with the reference's
+    quadrilateral convergence study (examples/study1/conv_study_square.csv)."""
+    from . import fe
+    m = sp.model
+    d = sp.T.cell_dofs
+    off = sp.offsets[2]
+    Tc = np.where(d > 0, x[off + np.maximum(d, 1) - 1], sp.T.diri_values[np.maximum(-d, 1) - 1])
+    vc, cv = m.vertex_coords, m.cell_vertices
+    cand = np.nonzero(np.isclose(vc[cv][:, :, 1], 0.0).sum(axis=1) >= 2)[0]
+    out = []
+    for X in np.linspace(0.0, 1.0, n_plot)[:-1]:
+        for c in cand:
+            P = vc[cv[c]]
+            if m.cell_type == fe.TRI:
+                A = np.array([P[1] - P[0], P[2] - P[0]]).T          # x = P0 + A (xi, eta)
+                r = np.linalg.solve(A, np.array([X, 0.0]) - P[0])
+                if r[0] < -1e-12 or r[1] < -1e-12 or r[0] + r[1] > 1 + 1e-12:
+                    continue
+                _, dphi = fe.shape_at(fe.TRI, r[0], r[1])
+                out.append(-np.linalg.solve(A.T, dphi.T @ Tc[c])[1])
+            else:
+                x0, x1 = P[:, 0].min(), P[:, 0].max()
+                if X < x0 - 1e-12 or X > x1 + 1e-12:
+                    continue
+                _, dphi = fe.shape_at(fe.QUAD, (X - x0) / (x1 - x0), 0.0)
+                out.append(-(dphi[:, 1] @ Tc[c]) / (P[:, 1].max() - P[:, 1].min()))
+            break
+    assert len(out) == n_plot - 1
+    return float(np.mean(out))
+
+
 # --------------------------------------------------------------------------------------
 # entropy fields of /root/reference/src/Solver.jl:281-289, sampled like examples/study1/study1.jl:251-271
 # (used only to pin the oracle's VELOCITY field against conv_study_square.csv: Sth_max, Sfl_max)

@@ -40,6 +40,24 @@ def test_golden_newton_62(gm):
     assert abs(gm.solver.nu_bot_avg(sp, res.x) - NU_GOLD[62]) / NU_GOLD[62] < 1e-13
 
 
+def test_triangle_discretisation_converges_to_the_reference_nusselt_number(gm):
+    """'TRI path pinned only by self-consistency (..., quad-vs-tri convergence to the same Nu)'.  The study-1 problem
+    (wave BCs, n = 0.6, Ra = 1e4, Pr = 100) on 2 x 32 x 32 jittered triangles: Newton on the oracle converges and Nu_bot_avg lies
+    within 1 % of the finest value of the reference's quadrilateral convergence study (conv_study_square.csv:6: 6.6189; the
+    study itself still moves by 0.06 % between its last two meshes).  A wrong triangle quadrature rule or node order changes
+    Nu at O(1)."""
+    from orc_operator import OracleOperator
+    prm = dict(Pr=100.0, Ra=1e4, n=0.6)
+    spq = cases.cart(12, bc=cases.WAVE)
+    rq = gm.solver.newton(OracleOperator(spq, **prm), np.zeros(spq.n_total), ftol=1e-8, xtol=1e-50, iterations=80)
+    assert abs(gm.solver.nu_bot_avg_generic(spq, rq.x) - gm.solver.nu_bot_avg(spq, rq.x)) < 1e-12   # same functional on quads
+    spt = cases.spaces(fe.square_tri_model(32, jitter=0.25, seed=1), cases.WAVE)
+    rt = gm.solver.newton(OracleOperator(spt, **prm), np.zeros(spt.n_total), ftol=1e-8, xtol=1e-50, iterations=80)
+    assert rt.residual_norm < 1e-6
+    nu = gm.solver.nu_bot_avg_generic(spt, rt.x)
+    assert abs(nu - 6.618933375624088) / 6.618933375624088 < 0.01, nu
+
+
 @pytest.mark.parametrize("n", [0.6, 1.0, 1.4])
 @pytest.mark.parametrize("kind", ["quad", "jquad", "tri"])
 def test_jacobian_is_derivative_of_residual(kind, n):
