@@ -11,10 +11,13 @@
 //               Entries go to a cell-major intermediate `cm` ([cell][major][minor], only the touched blocks: 360 / 783 doubles
 //               per TRI / QUAD cell); the pressure space is discontinuous, so the lists of pressure majors are complete after
 //               one cell and are written straight into nzval (and the pressure residual into b).
-//   k_lists   : one warp per velocity / temperature major dof.  Its incident (cell, local index) pairs are walked in ascending
-//               cell id -- Gridap's own accumulation order (SparseMatrixAssembler's cell loop) -- and the segments of `cm` are
-//               added into the list in shared memory at the positions of the compressed cell->nnz map (`grank`), then the
-//               list is stored once.  The residual entry is the same ordered sum over the cell residuals `cr`.
+//   k_lists   : one warp per group of four consecutive velocity / temperature major dofs (their lists are adjacent in nzval).  The
+//               incident (cell, local index) pairs of a major are walked in ascending cell id -- Gridap's own accumulation order
+//               (SparseMatrixAssembler's cell loop) -- and the segments of `cm` are added into the list in shared memory at the
+//               positions of the compressed cell->nnz map (`grank`); the four lists are then stored once, as one contiguous
+//               range.  No atomics: the result is bit-reproducible.  The residual entry is the same ordered sum over the cell
+//               residuals `cr`.  Everything about a major sits in one 64-byte record (GgDesc); the groups are processed in an
+//               order built at pattern time (gm_gather.cuh): locality windows of cells, long groups first.
 //
 // Layout of a cell's NEC = 2NN*LD + 3NN*NN intermediate values (cm) and map entries (grank):
 //   [U majors: 2NN x LD minors][T majors: NN x (2NN velocity + NN temperature minors)]; cell residuals: cr[cell][LD]
@@ -33,7 +36,6 @@
 
 #include "gm_const.h"
 
-#define GG_MAXLIST 320  // = GM_MAXCAND of gm_pattern.cuh
 #define GG_LWARPS 8     // warps per CTA of k_lists
 
 struct GgArgs {
@@ -55,8 +57,8 @@ struct GgArgs {
   double *nz, *b;
   unsigned flags;
   int nbatch;   // ceil(ncells / CPB)
-  int lstride;  // doubles of shared memory per warp of k_lists (>= 96, >= the longest list)
-  const struct GgDesc *desc;  // [ngroup][GG_MPW] records of the velocity / temperature majors, groups sorted by first incident cell
+  int lstride;  // doubles of shared memory per major of k_lists (>= the longest list; a warp holds GG_MPW lists)
+  const struct GgDesc *desc;  // [ngroup][GG_MPW] records of the velocity / temperature majors; groups with work only, in processing order
   int64_t ngroup;
 };
 
