@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define GM_VERSION 100 /* 0.1.0 */
+#define GM_VERSION 110 /* 0.1.1: gm_desc grew (n_own_cells, ghost_cell_ids), GM_PATH_GATHER */
 
 enum gm_status {
   GM_OK = 0,

@@ -16,7 +16,7 @@ def test_exports_match_header(gm):
     L = gm.capi.lib()
     for name in declared:
         assert hasattr(L, name)
-    assert L.gm_version() == 100
+    assert L.gm_version() == 110
 
 
 def test_desc_struct_size(gm):
