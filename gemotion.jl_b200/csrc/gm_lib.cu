@@ -353,7 +353,12 @@ extern "C" int gm_pattern(gm_handle *h, int64_t *nnz) {
     }
     if (h->active_path == GM_PATH_GATHER) {
       rc = gm_gather_after_pattern(h);
-      if (rc) return rc;
+      if (rc) {  // (e.g. the cell-matrix workspace does not fit): no half-built state; gm_assemble then reports the missing workspaces
+        gm_gather *g = (gm_gather *)h->gather;
+        if (g) { cudaFree(g->d_const); cudaFree(g->cm); cudaFree(g->cr); cudaFree(g->desc); delete g; }
+        h->gather = nullptr;
+        return rc;
+      }
     }
     rc = gm_touched_runs(h);
     if (rc) return rc;
