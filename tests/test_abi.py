@@ -34,3 +34,31 @@ def test_no_cpu_fallback(gm):
     sp = cases.cart(3)
     with pytest.raises(gm.capi.GmError):
         gm.operator.B200FEOperator(sp)
+
+
+def test_ctypes_structs_match_the_header(gm, tmp_path):
+    """sizeof / field offsets of gm_desc, gm_post_desc and gm_times as the C compiler sees include/gemotion_b200.h must equal the
+    ctypes mirrors in capi.py (gm_create only checks struct_size at run time, on a GPU box)."""
+    import ctypes as C
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "sz.c"
+    fields = {"gm_desc": ["struct_size", "ncells", "cartesian", "origin", "coords", "layout", "cell_dofs_u", "n_free", "diri_u", "nq", "w", "dgphi",
+                          "device", "rank", "cell_begin", "ghost_lo", "kernel", "n_own_cells", "ghost_cell_ids"],
+              "gm_times": ["h2d_ms", "exchange_ms", "launches", "d2h_bytes"],
+              "gm_post_desc": ["struct_size", "cell_dofs_psi", "diri_pi", "w2", "dphi4", "cell_nodes", "n_nodes"]}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "include/gemotion_b200.h"', 'int main(void) {']
+    for st, fl in fields.items():
+        lines.append('  printf("%s %%zu\\n", sizeof(%s));' % (st, st))
+        for f in fl:
+            lines.append('  printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (st, f, st, f))
+    lines += ['  return 0;', '}']
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", root, "-o", str(exe), str(src)])
+    out = dict(l.split() for l in subprocess.check_output([str(exe)]).decode().splitlines())
+    mirrors = {"gm_desc": gm.capi.gm_desc, "gm_times": gm.capi.gm_times, "gm_post_desc": gm.capi.gm_post_desc}
+    for st, fl in fields.items():
+        assert int(out[st]) == C.sizeof(mirrors[st]), st
+        for f in fl:
+            assert int(out["%s.%s" % (st, f)]) == getattr(mirrors[st], f).offset, (st, f)
