@@ -62,3 +62,25 @@ def test_ctypes_structs_match_the_header(gm, tmp_path):
         assert int(out[st]) == C.sizeof(mirrors[st]), st
         for f in fl:
             assert int(out["%s.%s" % (st, f)]) == getattr(mirrors[st], f).offset, (st, f)
+
+
+def test_julia_struct_mirrors_gm_desc(gm):
+    """julia/B200FEOperator.jl cannot be executed here (no Julia); its `struct GmDesc` must at least list the fields of gm_desc in
+    the same order with types of the same size and alignment (Julia lays an immutable struct of isbits fields out like C)."""
+    import ctypes as C
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    txt = open(os.path.join(root, "julia", "B200FEOperator.jl")).read()
+    body = txt[txt.index("struct GmDesc") + len("struct GmDesc"):]
+    body = body[:body.index("\nend")]
+    body = re.sub(r"#.*", "", body)
+    jl = re.findall(r"(\w+)::([\w{},]+)", body)
+    size = {"Int32": (4, 4), "Int64": (8, 8), "NTuple{2,Float64}": (16, 8), "NTuple{3,Int64}": (24, 8)}
+    off = 0
+    cfields = gm.capi.gm_desc._fields_
+    assert [n for n, _ in jl] == [f[0] for f in cfields]
+    for (name, ty), cf in zip(jl, cfields):
+        sz, al = (8, 8) if ty.startswith("Ptr{") else size[ty]
+        off = (off + al - 1) // al * al
+        assert off == getattr(gm.capi.gm_desc, name).offset and sz == C.sizeof(cf[1]), name
+        off += sz
+    assert (off + 7) // 8 * 8 == C.sizeof(gm.capi.gm_desc)
