@@ -84,3 +84,20 @@ def test_julia_struct_mirrors_gm_desc(gm):
         assert off == getattr(gm.capi.gm_desc, name).offset and sz == C.sizeof(cf[1]), name
         off += sz
     assert (off + 7) // 8 * 8 == C.sizeof(gm.capi.gm_desc)
+
+
+def test_header_is_plain_c_and_links(gm, tmp_path):
+    """include/gemotion_b200.h must be usable from plain C (the boundary a cgo / ccall / ctypes binding sees): a C11 translation
+    unit that takes the address of every declared entry point compiles with -Wall -Werror -pedantic and links against the library."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "gemotion_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(gm_[a-z0-9_]+)\s*\(", hdr)) - {"gm_desc", "gm_times"})
+    src = tmp_path / "use.c"
+    src.write_text('#include "include/gemotion_b200.h"\n#include <stdio.h>\nint main(void) {\n  void *p[] = {%s};\n'
+                   '  gm_desc d; d.struct_size = (int32_t)sizeof d; (void)d;\n  printf("%%d %%zu\\n", gm_version(), sizeof p / sizeof p[0]);\n  return 0;\n}\n'
+                   % ", ".join("(void *)%s" % n for n in names))
+    lib_dir = os.path.join(root, "gemotion.jl_b200")
+    exe = tmp_path / "use"
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-I", root, "-o", str(exe), str(src),
+                           "-L", lib_dir, "-l:libgemotion_b200.so", "-Wl,-rpath," + lib_dir])
