@@ -4,7 +4,7 @@
 # GeMotion manifest:
 #     julia --project=/path/to/GeMotion.jl bench/gridap_baseline.jl [N ...]          (default N = 256 512 1024)
 # It prints one JSON line per size in bench.py's vocabulary ("impl": "gridap"; Gridap's assembly loop is serial: "cores": 1), and, when
-# the library is on LD_LIBRARY_PATH (GM_B200_LIB), times the same calls through julia/B200FEOperator.jl beside it.
+# the library is on LD_LIBRARY_PATH (GEMOTION_B200_LIB), times the same calls through julia/B200FEOperator.jl beside it.
 using Gridap, Gridap.FESpaces, Gridap.Algebra, SparseArrays, Statistics, Printf
 
 sizes = isempty(ARGS) ? [256, 512, 1024] : parse.(Int, ARGS)
@@ -53,7 +53,7 @@ for N in sizes
   @printf("{\"impl\": \"gridap\", \"metric\": \"Jacobian+residual assembly Mcells/s (fp64)\", \"value\": %.6g, \"unit\": \"Mcells/s\", \"cores\": 1, \"mesh\": %d, \"ncells\": %d, \"n_free\": %d, \"nnz\": %d, \"ms_per_step\": %.3f, \"jacobian_only_ms\": %.3f, \"residual_only_ms\": %.3f, \"threads\": %d}\n",
           ncells / t_both / 1e6, N, ncells, nfree, nnz(A), 1e3 * t_both, 1e3 * t_jac, 1e3 * t_res, Threads.nthreads())
 
-  if haskey(ENV, "GM_B200_LIB")                                                         # the drop-in beside it, same calls, host arrays in / out
+  if haskey(ENV, "GEMOTION_B200_LIB")                                                         # the drop-in beside it, same calls, host arrays in / out
     include(joinpath(@__DIR__, "..", "julia", "B200FEOperator.jl"))
     opb = B200Assembly.B200FEOperator(X, Y, model, dΩ; Pr=Pr, Ra=Ra, n=n, jac_scaling=jac_scaling)
     bb, Ab = residual_and_jacobian(opb, uh)
