@@ -22,6 +22,11 @@ static inline int32_t gg_shfl_i(int32_t v, int src) {  // all 32 threads of the 
 }
 #include "../../gemotion.jl_b200/csrc/gm_gather_kernel.cuh"
 
+// partitioned mesh (gm_desc.n_own_cells / ghost_cell_ids): global ids of the local cells; a major is assembled iff its
+// lowest-numbered incident cell is an own cell (k_gg_desc's rule)
+static int64_t g_cell_begin = 0;
+static const int64_t *g_ghost_ids = nullptr;
+
 template <int NN, int NQ, int NV>
 static int run(GgArgs a, bool csr, int grid) {
   constexpr int CPB = 16;
@@ -50,6 +55,14 @@ static int run(GgArgs a, bool csr, int grid) {
       const int64_t a0 = a.adjptr[j];
       d.p0 = a.ptr[j]; d.j = (int32_t)j;
       d.len = (int32_t)(a.ptr[j + 1] - d.p0); d.cnt = (int32_t)(a.adjptr[j + 1] - a0);
+      if (g_ghost_ids) {
+        int64_t lowest = INT64_MAX;
+        for (int t = 0; t < d.cnt; ++t) {
+          const int64_t lc = a.adj[a0 + t] / ld, gc = lc < a.nown ? g_cell_begin + lc : g_ghost_ids[lc - a.nown];
+          lowest = std::min(lowest, gc);
+        }
+        if (!(lowest >= g_cell_begin && lowest < g_cell_begin + a.nown)) { d.cnt = 0; d.j = -1; }
+      }
       for (int t = 0; t < 10; ++t) d.e[t] = t < d.cnt ? gg_seg<NN>(a.adj[a0 + t]) : 0;
       maxlen = std::max(maxlen, (int)d.len);
     }
@@ -70,7 +83,8 @@ extern "C" int emu_gather_run(int nn, int64_t ncells, int64_t nU, int64_t oT, in
                               const double *coords, const int32_t *cellv, const int64_t *ptr, const uint16_t *grank, const uint16_t *grankp, int grid,
                               const int64_t *adjptr, const int32_t *adj, const double *x, double *nz, double *b, unsigned flags, int csr,
                               const double *prm /*Pr Ra n reg gx gy js*/, int cartesian, double hx, double hy, const double *w,
-                              const double *phi, const double *dphi, const double *psi, const double *dgphi) {
+                              const double *phi, const double *dphi, const double *psi, const double *dgphi,
+                              int64_t nown, int64_t cell_begin, const int64_t *ghost_ids) {
   const int nq = nn == 9 ? 4 : 3, nv = nn == 9 ? 4 : 3, ld = 3 * nn + 3;
   static GmConst c;
   memset(&c, 0, sizeof c);
@@ -85,7 +99,8 @@ extern "C" int emu_gather_run(int nn, int64_t ncells, int64_t nU, int64_t oT, in
   // poisoned workspaces: an entry k_cellmat does not write, or k_lists reads from the wrong place, shows up as a huge number
   std::vector<double> cm((size_t)(ncells * nec), 1e300), cr((size_t)(ncells * ld), 1e300);
   GgArgs a;
-  a.ncells = ncells; a.nown = ncells; a.nU = nU; a.oT = oT; a.n = n; a.gc = &c;
+  a.ncells = ncells; a.nown = nown > 0 ? nown : ncells; a.nU = nU;
+  g_cell_begin = cell_begin; g_ghost_ids = (nown > 0 && nown < ncells) ? ghost_ids : nullptr; a.oT = oT; a.n = n; a.gc = &c;
   a.gdofs = gdofs; a.dvals = dvals; a.coords = coords; a.cellv = cellv; a.ptr = ptr; a.grank = grank; a.grankp = grankp; a.adjptr = adjptr; a.adj = adj;
   a.x = x; a.cm = cm.data(); a.cr = cr.data(); a.nz = nz; a.b = b; a.flags = flags;
   return nn == 9 ? run<9, 4, 4>(a, csr != 0, grid) : run<6, 3, 3>(a, csr != 0, grid);

@@ -89,7 +89,7 @@ def run_emu(emu, sp, prm, layout, x, flags=3, grid=3):
     nn = 9 if m.cell_type == fe.QUAD else 6
     g, dv = global_dofs(sp)
     orc = Oracle(sp, **prm)
-    ptr, idx = orc.pattern(layout)
+    ptr, idx = orc.pattern(layout)   # (a rank of a partition: the pattern of its local tables)
     n = sp.n_total
     grank, grankp, adjptr, adj = gather_tables(g, nn, ptr, idx, n)
     nz, b = np.full(int(ptr[-1]), 7e77), np.full(n, 7e77)
@@ -104,13 +104,16 @@ def run_emu(emu, sp, prm, layout, x, flags=3, grid=3):
     else:
         hx = hy = 0.0
         coords = np.ascontiguousarray(m.vertex_coords, dtype=np.float64)
-        cellv = np.ascontiguousarray(m.cell_vertices, dtype=np.int32)
+        cellv = np.ascontiguousarray(m.cell_vertices if sp.cells is None else m.cell_vertices[sp.cells], dtype=np.int32)
+    part = getattr(sp, "part", None)
+    nown, cbeg, ghosts = (part[1] - part[0], part[0], np.ascontiguousarray(part[2], dtype=np.int64)) if part is not None else (0, 0, None)
     off = sp.offsets
     rc = emu.emu_gather_run(C.c_int(nn), C.c_int64(g.shape[0]), C.c_int64(off[1]), C.c_int64(off[2]), C.c_int64(n), _p(g), _p(dv),
                             _p(coords), _p(cellv), _p(ptr), _p(grank), _p(grankp), C.c_int(grid), _p(adjptr), _p(adj), _p(x), _p(nz), _p(b), C.c_uint(flags),
                             C.c_int(1 if layout == "csr" else 0), _p(pv), C.c_int(cart), C.c_double(hx), C.c_double(hy),
                             _p(np.ascontiguousarray(ref.w)), _p(np.ascontiguousarray(ref.phi)), _p(np.ascontiguousarray(ref.dphi)),
-                            _p(np.ascontiguousarray(ref.psi)), _p(np.ascontiguousarray(ref.dgphi)))
+                            _p(np.ascontiguousarray(ref.psi)), _p(np.ascontiguousarray(ref.dgphi)),
+                            C.c_int64(nown), C.c_int64(cbeg), _p(ghosts))
     assert rc == 0
     return orc, ptr, idx, nz, b
 
@@ -150,3 +153,26 @@ def test_gather_kernels_jacobian_only_and_residual_only(emu):
     _, _, _, nz2, b2 = run_emu(emu, sp, PARAMS[0], "csc", x, flags=2)
     assert np.array_equal(nz1, nz) and np.all(b1 == 7e77)
     assert np.array_equal(b2, b) and np.all(nz2 == 7e77)
+
+
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_gather_kernels_on_cell_range_ranks(emu, nranks):
+    """gm_desc.n_own_cells / ghost_cell_ids: every rank assembles, from its own + ghost cells, exactly the global lists and
+    residual entries of the dofs it owns (pressure rows only from own cells, records of unowned majors without incident cells)."""
+    model = fe.square_tri_model(7, jitter=0.25, seed=3)
+    spg = cases.spaces(model, cases.TURAN)
+    prm = PARAMS[2]
+    x = fe.splitmix_iterate(spg.n_total, 21)
+    orc = Oracle(spg, **prm)
+    optr, oidx = orc.pattern("csc")
+    onz, ob = orc.assemble(x, "csc")
+    got_nz, got_b = np.full(onz.size, np.nan), np.full(ob.size, np.nan)
+    for r in range(nranks):
+        sp = fe.build_rank_spaces_cells(model, cases.TURAN["V"], cases.TURAN["Ttags"], cases.TURAN["Texpr"], r, nranks)
+        _, ptr, idx, nz, b = run_emu(emu, sp, prm, "csc", x)
+        for dof in fe.owned_dofs(sp):
+            assert np.array_equal(idx[ptr[dof]:ptr[dof + 1]], oidx[optr[dof]:optr[dof + 1]])
+            got_nz[optr[dof]:optr[dof + 1]] = nz[ptr[dof]:ptr[dof + 1]]
+            got_b[dof] = b[dof]
+    assert cases.block_scaled_err(got_nz, onz, cases.nz_blocks(spg, optr, oidx)) <= TOL
+    assert cases.block_scaled_err(got_b, ob, cases.res_blocks(spg)) <= TOL
